@@ -1,0 +1,154 @@
+/*
+ * agd_b200.h -- C-ABI of the B200-native accelerated-gradient-descent hot path.
+ *
+ * This is the drop-in boundary a JVM binding (JNI) for staple/spark-agd would bind: plain
+ * pointers and sizes, no C++/torch types.  Reference paths are relative to /root/reference:
+ *   AGD.scala   = src/main/scala/org/apache/spark/mllib/optimization/AcceleratedGradientDescent.scala
+ *   Suite.scala = src/test/scala/org/apache/spark/mllib/optimization/AcceleratedGradientDescentSuite.scala
+ *
+ * Model: one agd_handle per process owns one or more local B200s.  Each GPU pins one row-shard of
+ * the (n x d) design matrix in HBM (the analogue of `dataRDD.cache()`, Suite.scala:51).  A "pass" is
+ * one applySmooth (AGD.scala:192-208): fused row-block gradient kernel over the shard, one
+ * all-reduce of the packed [grad(d) | loss | count] fp64 buffer, and the fused O(d) update kernel.
+ * All entry points return 0 on success, nonzero on error (see agd_last_error).  There is no CPU
+ * fallback anywhere: without a usable sm_100 GPU every compute entry point fails.
+ *
+ * Threading: agd_reserve / agd_load_* may be called concurrently for DIFFERENT local devices (Spark
+ * task threads); everything else is single-caller, like the driver thread of AGD.scala:177.
+ * Ownership: the caller owns every host buffer; the library owns device memory until agd_destroy.
+ */
+#ifndef AGD_B200_H
+#define AGD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGD_B200_ABI_VERSION 1
+
+typedef struct agd_handle agd_handle;
+
+/* Closed enum of the Gradient plug-ins the reference can be given (AGD.scala:41,198):
+ * LogisticGradient (binary), LeastSquaresGradient, HingeGradient of spark-mllib 1.3.0.
+ * AGD_GRAD_LEAST_SQUARES_HALF is the Spark >= 1.4 definition (loss diff^2/2, gradient diff*x). */
+enum { AGD_GRAD_LOGISTIC = 0, AGD_GRAD_LEAST_SQUARES = 1, AGD_GRAD_HINGE = 2, AGD_GRAD_LEAST_SQUARES_HALF = 3 };
+/* Closed enum of the Updater plug-ins (AGD.scala:41,215): SimpleUpdater, SquaredL2Updater, L1Updater. */
+enum { AGD_UPD_SIMPLE = 0, AGD_UPD_SQUARED_L2 = 1, AGD_UPD_L1 = 2 };
+/* Element types: host source type and HBM storage type of the design matrix. */
+enum { AGD_F64 = 0, AGD_F32 = 1, AGD_BF16 = 2 };
+/* agd_params.flags */
+enum {
+  AGD_FLAG_MEMOIZE_FX = 1, /* reuse (f_x, g_x) of AGD.scala:269 for the history pass at :304 when x is
+                              unchanged (bit-identical result, 3 -> 2 passes per iteration) */
+};
+
+/* The constructor arguments + eight hyper-parameters of AGD.scala:41-51 (defaults: agd_default_params). */
+typedef struct {
+  double convergence_tol; /* AGD.scala:44  default 1e-4 */
+  int32_t num_iterations; /* AGD.scala:45  default 100  */
+  double reg_param;       /* AGD.scala:46  default 0.0  */
+  double L0;              /* AGD.scala:47  default 1.0  */
+  double Lexact;          /* AGD.scala:48  default +inf */
+  double beta;            /* AGD.scala:49  default 0.5  */
+  double alpha;           /* AGD.scala:50  default 0.9  */
+  int32_t may_restart;    /* AGD.scala:51  default 1    */
+  int32_t gradient;       /* AGD_GRAD_*  (the `gradient` delegate, AGD.scala:41) */
+  int32_t updater;        /* AGD_UPD_*   (the `updater` delegate,  AGD.scala:41) */
+  int32_t flags;          /* AGD_FLAG_*; 0 reproduces the reference's pass structure exactly */
+} agd_params;
+
+/* What `run` learned; the reference only logs (AGD.scala:310,334). */
+typedef struct {
+  int32_t iterations;     /* = length of the loss history */
+  int32_t passes;         /* applySmooth evaluations executed */
+  int32_t backtracks;     /* times AGD.scala:292 raised L */
+  int32_t restarts;       /* times AGD.scala:327-331 fired */
+  int32_t converged;      /* left through AGD.scala:319 or :323 */
+  int32_t stopped_nan;    /* left through AGD.scala:309-312 */
+  int32_t nonterminating; /* L became NaN: the reference would spin forever in :246-293; we stop */
+  int32_t reserved0;
+  double final_L;
+  double final_theta;
+  double seconds_total;   /* host wall time inside agd_run */
+  double k1_ms_total;     /* CUDA-event time of the gradient kernel (device 0), all passes */
+  int64_t k1_launches;    /* launches of the gradient kernel per device */
+  int64_t gpu_launches;   /* all kernel launches issued by this call, per device */
+  double allreduce_ms_total; /* CUDA-event time of the all-reduce (0 when world == 1) */
+} agd_stats;
+
+/* ---- lifecycle ---- */
+int agd_abi_version(void);
+/* sizeof(agd_params) / sizeof(agd_stats) as compiled, so a foreign binding can verify its struct layout */
+int agd_sizeof_params(void);
+int agd_sizeof_stats(void);
+void agd_default_params(agd_params *p);
+/* Opens n_dev local GPUs (device ordinals in device_ids).  Fails when a device is not sm_100. */
+int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out);
+int agd_destroy(agd_handle *h);
+/* Message of the last failure on this handle (h may be NULL: last agd_create failure). */
+const char *agd_last_error(const agd_handle *h);
+
+/* ---- the collective (replaces treeAggregate + broadcast, AGD.scala:193,196-204) ----
+ * One rank per GPU.  With a single process owning all GPUs nothing needs to be called (agd_create
+ * builds the communicator).  With one process per GPU (torchrun / one executor per GPU): rank 0
+ * calls agd_comm_unique_id, ships the 128 bytes to every process, and every process calls
+ * agd_comm_init(h, id, world_ranks, first_rank) where its local GPUs take ranks
+ * first_rank .. first_rank + n_dev - 1. */
+int agd_comm_unique_id(void *out128);
+int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t first_rank);
+
+/* ---- shard loading (replaces RDD[(Double, Vector)] partitions cached on executors, AGD.scala:178) ----
+ * agd_reserve fixes the shard geometry of local device `dev` and allocates HBM for `rows_capacity`
+ * rows stored as `store_dtype` (AGD_F32 or AGD_F64).  agd_load_dense APPENDS `rows` rows (row-major,
+ * leading dimension ld elements, element type src_dtype AGD_F64|AGD_F32) and their labels.  If the
+ * device was not reserved, the first load reserves exactly `rows`. */
+int agd_reserve(agd_handle *h, int32_t dev, int64_t rows_capacity, int32_t d, int32_t store_dtype);
+int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype, const double *labels,
+                   int64_t rows, int32_t d, int64_t ld, int32_t store_dtype);
+/* SparseVector rows as CSR (values src_dtype AGD_F64|AGD_F32, stored as store_dtype). */
+int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_t *idx, const void *val,
+                 int32_t src_dtype, const double *labels, int64_t rows, int32_t d, int32_t store_dtype);
+/* Drops every shard (all local devices). */
+int agd_clear(agd_handle *h);
+/* Rows currently resident on local device `dev`; feature count (0 when empty). */
+int64_t agd_rows(const agd_handle *h, int32_t dev);
+int32_t agd_dim(const agd_handle *h);
+
+/* ---- measurement harness (not in the reference): synthetic workload generated in place ----
+ * Every GPU rank r of the world fills its shard with global rows [r*total_rows/W, (r+1)*total_rows/W)
+ * of the counter-based synthetic design matrix (spec: spark-agd_b200/csrc/synth.cu) and labels for
+ * `gradient`.  agd_get_rows downloads rows (as the storage dtype) and labels for checking. */
+int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dtype, uint64_t seed,
+                 int32_t gradient);
+int agd_get_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, void *X_out, double *labels_out);
+int agd_synth_wtrue(agd_handle *h, uint64_t seed, int32_t d, double *w_out);
+
+/* ---- plug-in granularity entry points (host buffers in and out) ----
+ * agd_smooth = applySmooth (AGD.scala:192-208): loss/count and grad/count over ALL shards of the
+ * world; w, grad are d doubles on the host.  Every rank must call it. */
+int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, double *grad, int64_t *count);
+/* agd_prox = applyProjector (AGD.scala:214-222): Updater.compute(w, g, step, iter = 1, reg). */
+int agd_prox(agd_handle *h, int32_t updater, const double *w, const double *g, double step, double reg,
+             int32_t d, double *w_out, double *reg_val);
+
+/* ---- the whole loop, natively: AcceleratedGradientDescent.run (AGD.scala:177-338) ----
+ * w0, w_out: d doubles.  loss_hist: capacity >= max(num_iterations, 1); *n_hist receives its length.
+ * Every rank must call it with identical arguments; every rank receives identical results. */
+int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out, double *loss_hist,
+            int32_t *n_hist, agd_stats *stats);
+
+/* GradientDescent.runMiniBatchSGD of spark-mllib 1.3.0 with miniBatchFraction = 1.0 (the comparator
+ * the reference's tests run beside AGD, Suite.scala:78,118,225), on the same kernels. */
+int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_size, int32_t num_iterations,
+               double reg_param, const double *w0, double *w_out, double *loss_hist, int32_t *n_hist,
+               agd_stats *stats);
+
+/* Kernel-variant override for experiments/benchmarks: name in {"auto","ring","generic"}. */
+int agd_set_option(agd_handle *h, const char *key, const char *value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGD_B200_H */

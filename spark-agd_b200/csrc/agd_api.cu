@@ -1,0 +1,933 @@
+// agd_api.cu -- the C-ABI of include/agd_b200.h: handle, shard loading, the collective, and the
+// AcceleratedGradientDescent.run driver loop (AGD.scala:177-338) executed natively around the
+// K1 / all-reduce / K3 kernels.  No CPU fallback: every compute entry point needs an sm_100 GPU.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only; the library is dlopen'ed (torch ships its own libnccl.so.2)
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <cmath>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "agd_common.cuh"
+
+using namespace agd;
+
+// ---------------------------------------------------------------- NCCL through dlopen
+namespace {
+
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+NcclApi &nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return; }
+#define AGD_NCCL_SYM(name)                                                   \
+  api.name = reinterpret_cast<decltype(api.name)>(dlsym(lib, "nccl" #name)); \
+  if (!api.name) { api.why = "missing symbol nccl" #name; return; }
+    AGD_NCCL_SYM(GetUniqueId)
+    AGD_NCCL_SYM(CommInitRank)
+    AGD_NCCL_SYM(AllReduce)
+    AGD_NCCL_SYM(GroupStart)
+    AGD_NCCL_SYM(GroupEnd)
+    AGD_NCCL_SYM(CommDestroy)
+    AGD_NCCL_SYM(GetErrorString)
+#undef AGD_NCCL_SYM
+    api.ok = true;
+  });
+  return api;
+}
+
+std::string g_create_error;
+std::mutex g_create_mu;
+
+struct Shard {
+  void *X = nullptr;          // dense, row-major, ld == d
+  double *labels = nullptr;   // cap + pad
+  int64_t rows = 0, cap = 0;
+  int elem_bytes = 0;         // 4 (fp32) or 8 (fp64) storage
+  bool csr = false;
+  int64_t *rowptr = nullptr;
+  int32_t *idx = nullptr;
+  void *val = nullptr;
+  int64_t nnz = 0;
+};
+
+struct Dev {
+  int ordinal = -1;
+  int sm_count = 0;
+  cudaStream_t st = nullptr;
+  Shard sh;
+  // d-vectors of the driver loop (AGD.scala:224-230,241,249) + packed pass result
+  double *x = nullptr, *z = nullptr, *x_old = nullptr, *z_old = nullptr, *y = nullptr, *g_y = nullptr,
+         *g_x = nullptr, *wtmp = nullptr, *acc = nullptr;
+  int32_t vec_d = 0;
+  double *slabs = nullptr;
+  size_t slabs_doubles = 0;
+  double *partials = nullptr;
+  unsigned int *ticket = nullptr;
+  double *scalars_dev = nullptr;
+  double *scalars_host = nullptr;  // pinned, 2*K3_NS
+  void *stage_dev = nullptr;
+  size_t stage_bytes = 0;
+  ncclComm_t comm = nullptr;
+  std::vector<cudaEvent_t> ev;     // K1 start/stop pairs (device 0 only)
+  size_t ev_used = 0;
+  std::vector<cudaEvent_t> ev_ar;  // all-reduce start/stop pairs
+  size_t ev_ar_used = 0;
+  std::mutex *mu = nullptr;
+};
+
+}  // namespace
+
+struct agd_handle {
+  std::vector<Dev> devs;
+  int32_t d = 0;
+  int world = 1, first_rank = 0;
+  bool comm_ready = false;
+  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic
+  int ring_stages = 0;
+  int tune_rows = 0, tune_ctas = 0;
+  std::string err;
+  std::mutex mu;
+  int64_t launches = 0;  // per device, current call
+};
+
+namespace {
+
+int fail(agd_handle *h, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else {
+    std::lock_guard<std::mutex> g(g_create_mu);
+    g_create_error = buf;
+  }
+  return 1;
+}
+
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKN(call)                                                                                        \
+  do {                                                                                                   \
+    ncclResult_t r_ = (call);                                                                            \
+    if (r_ != ncclSuccess) return fail(h, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+// Java Math.max / Math.min (NaN-propagating), used at AGD.scala:274,275,286,292,322
+double jmax(double a, double b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  if (a == 0.0 && b == 0.0) return std::signbit(a) ? b : a;
+  return a > b ? a : b;
+}
+double jmin(double a, double b) {
+  if (a != a) return a;
+  if (b != b) return b;
+  if (a == 0.0 && b == 0.0) return std::signbit(a) ? a : b;
+  return a < b ? a : b;
+}
+
+int dtype_bytes(int dt) { return dt == AGD_F64 ? 8 : (dt == AGD_F32 ? 4 : 0); }
+
+int free_shard(agd_handle *h, Dev &D) {
+  CK(cudaSetDevice(D.ordinal));
+  Shard &s = D.sh;
+  if (s.X) cudaFree(s.X);
+  if (s.labels) cudaFree(s.labels);
+  if (s.rowptr) cudaFree(s.rowptr);
+  if (s.idx) cudaFree(s.idx);
+  if (s.val) cudaFree(s.val);
+  s = Shard();
+  return 0;
+}
+
+int ensure_vectors(agd_handle *h, Dev &D, int32_t d) {
+  if (D.vec_d == d) return 0;
+  CK(cudaSetDevice(D.ordinal));
+  double **v[] = {&D.x, &D.z, &D.x_old, &D.z_old, &D.y, &D.g_y, &D.g_x, &D.wtmp};
+  for (double **p : v) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    CK(cudaMalloc(p, ((size_t)d + 2) * sizeof(double)));
+    CK(cudaMemsetAsync(*p, 0, ((size_t)d + 2) * sizeof(double), D.st));
+  }
+  if (D.acc) cudaFree(D.acc);
+  CK(cudaMalloc(&D.acc, ((size_t)d + 2) * sizeof(double)));
+  if (D.partials) cudaFree(D.partials);
+  CK(cudaMalloc(&D.partials, (size_t)k3_blocks(d) * K3_NS * sizeof(double)));
+  D.vec_d = d;
+  return 0;
+}
+
+int ensure_slabs(agd_handle *h, Dev &D, int blocks, int32_t d) {
+  const size_t need = (size_t)blocks * ((size_t)d + 1);
+  if (need <= D.slabs_doubles) return 0;
+  CK(cudaSetDevice(D.ordinal));
+  if (D.slabs) cudaFree(D.slabs);
+  D.slabs = nullptr;
+  CK(cudaMalloc(&D.slabs, need * sizeof(double)));
+  D.slabs_doubles = need;
+  return 0;
+}
+
+int set_dim(agd_handle *h, int32_t d) {
+  std::lock_guard<std::mutex> g(h->mu);
+  if (d <= 0) return fail(h, "feature dimension must be positive (got %d)", d);
+  if (h->d == 0) h->d = d;
+  else if (h->d != d) return fail(h, "feature dimension mismatch: shard has d=%d, call passed d=%d", h->d, d);
+  return 0;
+}
+
+int reserve_locked(agd_handle *h, Dev &D, int64_t cap, int32_t d, int store_dtype) {
+  const int eb = dtype_bytes(store_dtype);
+  if (!eb) return fail(h, "store_dtype must be AGD_F32 or AGD_F64");
+  if (cap < 0) return fail(h, "negative capacity");
+  CK(cudaSetDevice(D.ordinal));
+  Shard &s = D.sh;
+  if (s.csr) return fail(h, "device already holds a CSR shard");
+  if (s.cap > 0 && s.elem_bytes != eb) return fail(h, "storage dtype mismatch with the resident shard");
+  if (cap <= s.cap) return 0;
+  void *nx = nullptr;
+  double *nl = nullptr;
+  const size_t xbytes = (size_t)cap * d * eb + 64;
+  CK(cudaMalloc(&nx, xbytes));
+  CK(cudaMalloc(&nl, ((size_t)cap + 64) * sizeof(double)));
+  CK(cudaMemsetAsync(nl, 0, ((size_t)cap + 64) * sizeof(double), D.st));
+  if (s.rows > 0) {
+    CK(cudaMemcpyAsync(nx, s.X, (size_t)s.rows * d * eb, cudaMemcpyDeviceToDevice, D.st));
+    CK(cudaMemcpyAsync(nl, s.labels, (size_t)s.rows * sizeof(double), cudaMemcpyDeviceToDevice, D.st));
+  }
+  CK(cudaStreamSynchronize(D.st));
+  if (s.X) cudaFree(s.X);
+  if (s.labels) cudaFree(s.labels);
+  s.X = nx;
+  s.labels = nl;
+  s.cap = cap;
+  s.elem_bytes = eb;
+  return 0;
+}
+
+int ensure_stage(agd_handle *h, Dev &D, size_t bytes) {
+  if (D.stage_bytes >= bytes) return 0;
+  if (D.stage_dev) cudaFree(D.stage_dev);
+  D.stage_dev = nullptr;
+  CK(cudaMalloc(&D.stage_dev, bytes));
+  D.stage_bytes = bytes;
+  return 0;
+}
+
+cudaEvent_t next_event(std::vector<cudaEvent_t> &pool, size_t &used) {
+  if (used == pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pool.push_back(e);
+  }
+  return pool[used++];
+}
+
+// One applySmooth (AGD.scala:192-208) at the device-resident point `w_of(dev)`: K1 over every local
+// shard, slab reduction, one all-reduce of [grad | loss | count].  Result: Dev::acc on every device.
+template <typename WSel>
+int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
+  const int32_t d = h->d;
+  for (size_t i = 0; i < h->devs.size(); ++i) {
+    Dev &D = h->devs[i];
+    CK(cudaSetDevice(D.ordinal));
+    const Shard &s = D.sh;
+    const bool t0 = timed && i == 0;
+    if (s.csr) {
+      K1CsrArgs a;
+      a.rowptr = s.rowptr; a.idx = s.idx; a.val = s.val; a.labels = s.labels; a.w = w_of(D);
+      a.gacc = D.acc; a.rows = s.rows; a.d = d; a.kind = kind;
+      if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
+      CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
+      if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
+      h->launches += (i == 0) ? 2 : 0;
+      continue;
+    }
+    K1Args a;
+    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.rows = s.rows; a.d = d; a.kind = kind;
+    a.stages = h->ring_stages; a.slab_stride = d + 1; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas;
+    const int eb = s.elem_bytes ? s.elem_bytes : 4;
+    bool ring = k1_ring_supported(d, eb) != 0;
+    if (h->k1_variant == 2) ring = false;
+    if (h->k1_variant == 1 && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
+    int max_blocks = k1_max_blocks(D.sm_count);
+    if (!ring) {  // generic: bound the slab memory for very wide rows
+      const long long lim = (32LL << 20) / ((long long)d + 1);
+      if (lim < max_blocks) max_blocks = lim < 1 ? 1 : (int)lim;
+    }
+    if (ensure_slabs(h, D, max_blocks, d)) return 1;
+    a.slabs = D.slabs;
+    int blocks = 0;
+    if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
+    if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
+    else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
+    if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
+    CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, D.st));
+    if (i == 0) h->launches += (s.rows > 0 ? 2 : 1);
+  }
+  if (h->world > 1) {
+    if (!h->comm_ready) return fail(h, "world_ranks=%d but agd_comm_init was not called", h->world);
+    NcclApi &N = nccl_api();
+    Dev &D0 = h->devs[0];
+    if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
+    CKN(N.GroupStart());
+    for (Dev &D : h->devs) CKN(N.AllReduce(D.acc, D.acc, (size_t)d + 2, ncclDouble, ncclSum, D.comm, D.st));
+    CKN(N.GroupEnd());
+    if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
+    h->launches += 1;
+  }
+  return 0;
+}
+
+int read_scalars(agd_handle *h, double *out) {
+  Dev &D = h->devs[0];
+  CK(cudaSetDevice(D.ordinal));
+  CK(cudaMemcpyAsync(D.scalars_host, D.scalars_dev, K3_NS * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+  CK(cudaStreamSynchronize(D.st));
+  memcpy(out, D.scalars_host, K3_NS * sizeof(double));
+  return 0;
+}
+
+int sum_events(agd_handle *h, std::vector<cudaEvent_t> &pool, size_t used, double *ms_out) {
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < used; i += 2) {
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, pool[i], pool[i + 1]));
+    ms += t;
+  }
+  *ms_out = ms;
+  return 0;
+}
+
+int check_ready(agd_handle *h) {
+  if (!h) return 1;
+  if (h->d <= 0) return fail(h, "no shard loaded (call agd_load_dense / agd_load_csr / agd_generate first)");
+  for (Dev &D : h->devs)
+    if (ensure_vectors(h, D, h->d)) return 1;
+  return 0;
+}
+
+double reg_value(int updater, double reg, double sum_sq, double sum_abs) {
+  if (updater == AGD_UPD_SQUARED_L2) {
+    const double nrm = std::sqrt(sum_sq);  // brzNorm(w, 2.0)
+    return 0.5 * reg * nrm * nrm;
+  }
+  if (updater == AGD_UPD_L1) return sum_abs * reg;
+  return 0.0;
+}
+
+}  // namespace
+
+// ================================================================ C-ABI
+extern "C" {
+
+int agd_abi_version(void) { return AGD_B200_ABI_VERSION; }
+int agd_sizeof_params(void) { return (int)sizeof(agd_params); }
+int agd_sizeof_stats(void) { return (int)sizeof(agd_stats); }
+
+void agd_default_params(agd_params *p) {  // AGD.scala:44-51
+  memset(p, 0, sizeof *p);
+  p->convergence_tol = 1e-4;
+  p->num_iterations = 100;
+  p->reg_param = 0.0;
+  p->L0 = 1.0;
+  p->Lexact = std::numeric_limits<double>::infinity();
+  p->beta = 0.5;
+  p->alpha = 0.9;
+  p->may_restart = 1;
+  p->gradient = AGD_GRAD_LOGISTIC;
+  p->updater = AGD_UPD_SIMPLE;
+  p->flags = 0;
+}
+
+const char *agd_last_error(const agd_handle *h) {
+  if (h) return h->err.c_str();
+  return g_create_error.c_str();
+}
+
+int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
+  agd_handle *h = nullptr;  // errors before the handle exists go to the global slot
+  if (!out) return fail(h, "out is NULL");
+  *out = nullptr;
+  if (n_dev < 1 || !device_ids) return fail(h, "need at least one device");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(h, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  agd_handle *nh = new agd_handle();
+  nh->devs.resize(n_dev);
+  for (int i = 0; i < n_dev; ++i) {
+    Dev &D = nh->devs[i];
+    D.ordinal = device_ids[i];
+    D.mu = new std::mutex();
+    if (D.ordinal < 0 || D.ordinal >= count) { fail(h, "device ordinal %d out of range (0..%d)", D.ordinal, count - 1); agd_destroy(nh); return 1; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, D.ordinal) != cudaSuccess || prop.major != 10) {
+      fail(h, "device %d is not an sm_100 (Blackwell B200) GPU; kernels are built for sm_100a only", D.ordinal);
+      agd_destroy(nh);
+      return 1;
+    }
+    D.sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(D.ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&D.ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(D.ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&D.scalars_dev, 2 * K3_NS * sizeof(double)) != cudaSuccess ||
+        cudaMemset(D.scalars_dev, 0, 2 * K3_NS * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&D.scalars_host, 2 * K3_NS * sizeof(double)) != cudaSuccess) {
+      fail(h, "device %d setup failed: %s", D.ordinal, cudaGetErrorString(cudaGetLastError()));
+      agd_destroy(nh);
+      return 1;
+    }
+  }
+  nh->world = n_dev;
+  nh->first_rank = 0;
+  *out = nh;
+  if (n_dev > 1) {  // single-process owner of several GPUs: build the communicator now
+    unsigned char id[128];
+    if (agd_comm_unique_id(id) || agd_comm_init(nh, id, n_dev, 0)) {
+      fail(h, "communicator setup failed: %s", nh->err.c_str());
+      *out = nullptr;
+      agd_destroy(nh);
+      return 1;
+    }
+  }
+  return 0;
+}
+
+int agd_destroy(agd_handle *h) {
+  if (!h) return 0;
+  for (Dev &D : h->devs) {
+    cudaSetDevice(D.ordinal);
+    cudaStreamSynchronize(D.st);
+    if (D.comm && nccl_api().ok) nccl_api().CommDestroy(D.comm);
+    free_shard(h, D);
+    double *v[] = {D.x, D.z, D.x_old, D.z_old, D.y, D.g_y, D.g_x, D.wtmp, D.acc, D.slabs, D.partials, D.scalars_dev};
+    for (double *p : v)
+      if (p) cudaFree(p);
+    if (D.ticket) cudaFree(D.ticket);
+    if (D.scalars_host) cudaFreeHost(D.scalars_host);
+    if (D.stage_dev) cudaFree(D.stage_dev);
+    for (cudaEvent_t e : D.ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : D.ev_ar) cudaEventDestroy(e);
+    if (D.st) cudaStreamDestroy(D.st);
+    delete D.mu;
+  }
+  delete h;
+  return 0;
+}
+
+int agd_comm_unique_id(void *out128) {
+  agd_handle *h = nullptr;
+  NcclApi &N = nccl_api();
+  if (!N.ok) return fail(h, "NCCL unavailable: %s", N.why.c_str());
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  ncclResult_t r = N.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(h, "ncclGetUniqueId failed: %s", N.GetErrorString(r));
+  memcpy(out128, &id, 128);
+  return 0;
+}
+
+int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t first_rank) {
+  if (!h) return 1;
+  NcclApi &N = nccl_api();
+  if (!N.ok) return fail(h, "NCCL unavailable: %s", N.why.c_str());
+  const int nd = (int)h->devs.size();
+  if (world_ranks < nd || first_rank < 0 || first_rank + nd > world_ranks)
+    return fail(h, "bad rank layout: world=%d first=%d local=%d", world_ranks, first_rank, nd);
+  if (h->comm_ready) return fail(h, "communicator already initialised");
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  if (world_ranks > 1) {
+    CKN(N.GroupStart());
+    for (int i = 0; i < nd; ++i) {
+      CK(cudaSetDevice(h->devs[i].ordinal));
+      CKN(N.CommInitRank(&h->devs[i].comm, world_ranks, id, first_rank + i));
+    }
+    CKN(N.GroupEnd());
+  }
+  h->world = world_ranks;
+  h->first_rank = first_rank;
+  h->comm_ready = true;
+  return 0;
+}
+
+int agd_reserve(agd_handle *h, int32_t dev, int64_t rows_capacity, int32_t d, int32_t store_dtype) {
+  if (!h) return 1;
+  if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
+  if (set_dim(h, d)) return 1;
+  Dev &D = h->devs[dev];
+  std::lock_guard<std::mutex> g(*D.mu);
+  return reserve_locked(h, D, rows_capacity, d, store_dtype);
+}
+
+int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype, const double *labels,
+                   int64_t rows, int32_t d, int64_t ld, int32_t store_dtype) {
+  if (!h) return 1;
+  if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
+  const int sb = dtype_bytes(src_dtype);
+  if (!sb) return fail(h, "src_dtype must be AGD_F32 or AGD_F64");
+  if (rows < 0 || ld < d) return fail(h, "bad geometry rows=%lld d=%d ld=%lld", (long long)rows, d, (long long)ld);
+  if (rows > 0 && (!X || !labels)) return fail(h, "NULL data pointer");
+  if (set_dim(h, d)) return 1;
+  Dev &D = h->devs[dev];
+  std::lock_guard<std::mutex> g(*D.mu);
+  Shard &s = D.sh;
+  const int64_t need = s.rows + rows;
+  if (s.cap == 0 || need > s.cap) {
+    const int64_t cap = s.cap == 0 ? need : (need > 2 * s.cap ? need : 2 * s.cap);
+    if (reserve_locked(h, D, cap, d, s.cap ? (s.elem_bytes == 8 ? AGD_F64 : AGD_F32) : store_dtype)) return 1;
+  }
+  const int eb = s.elem_bytes;
+  if (dtype_bytes(store_dtype) != eb) return fail(h, "storage dtype mismatch with the resident shard");
+  CK(cudaSetDevice(D.ordinal));
+  unsigned char *dst = (unsigned char *)s.X + (size_t)s.rows * d * eb;
+  const unsigned char *src = (const unsigned char *)X;
+  if (rows > 0) {
+    if (sb == eb && ld == d) {
+      CK(cudaMemcpyAsync(dst, src, (size_t)rows * d * eb, cudaMemcpyHostToDevice, D.st));
+    } else {
+      int64_t chunk = (int64_t)((64u << 20) / ((size_t)ld * sb));
+      if (chunk < 1) chunk = 1;
+      if (chunk > rows) chunk = rows;
+      if (ensure_stage(h, D, (size_t)chunk * ld * sb)) return 1;
+      for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+        const int64_t rc = rows - r0 < chunk ? rows - r0 : chunk;
+        CK(cudaMemcpyAsync(D.stage_dev, src + (size_t)r0 * ld * sb, (size_t)rc * ld * sb, cudaMemcpyHostToDevice, D.st));
+        CK(convert_rows_launch(dst + (size_t)r0 * d * eb, eb, D.stage_dev, sb, rc, d, ld, D.st));
+        CK(cudaStreamSynchronize(D.st));  // the staging buffer is reused
+      }
+    }
+    CK(cudaMemcpyAsync(s.labels + s.rows, labels, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, D.st));
+  }
+  CK(cudaStreamSynchronize(D.st));
+  s.rows += rows;
+  return 0;
+}
+
+int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_t *idx, const void *val,
+                 int32_t src_dtype, const double *labels, int64_t rows, int32_t d, int32_t store_dtype) {
+  if (!h) return 1;
+  if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
+  const int sb = dtype_bytes(src_dtype), eb = dtype_bytes(store_dtype);
+  if (!sb || !eb) return fail(h, "dtypes must be AGD_F32 or AGD_F64");
+  if (rows < 0 || (rows > 0 && (!rowptr || !labels))) return fail(h, "bad CSR arguments");
+  if (set_dim(h, d)) return 1;
+  Dev &D = h->devs[dev];
+  std::lock_guard<std::mutex> g(*D.mu);
+  Shard &s = D.sh;
+  if (s.rows > 0 || s.cap > 0) return fail(h, "CSR shards are loaded in one call per device; call agd_clear first");
+  CK(cudaSetDevice(D.ordinal));
+  const int64_t nnz = rows > 0 ? rowptr[rows] - rowptr[0] : 0;
+  if (rows > 0 && rowptr[0] != 0) return fail(h, "rowptr[0] must be 0");
+  CK(cudaMalloc(&s.rowptr, ((size_t)rows + 1) * sizeof(int64_t)));
+  CK(cudaMalloc(&s.idx, ((size_t)nnz + 4) * sizeof(int32_t)));
+  CK(cudaMalloc(&s.val, ((size_t)nnz + 4) * eb));
+  CK(cudaMalloc(&s.labels, ((size_t)rows + 64) * sizeof(double)));
+  if (rows > 0) {
+    CK(cudaMemcpyAsync(s.rowptr, rowptr, ((size_t)rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemcpyAsync(s.labels, labels, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, D.st));
+  } else {
+    CK(cudaMemsetAsync(s.rowptr, 0, sizeof(int64_t), D.st));
+  }
+  if (nnz > 0) {
+    CK(cudaMemcpyAsync(s.idx, idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, D.st));
+    if (sb == eb) {
+      CK(cudaMemcpyAsync(s.val, val, (size_t)nnz * eb, cudaMemcpyHostToDevice, D.st));
+    } else {
+      if (ensure_stage(h, D, (size_t)nnz * sb)) return 1;
+      CK(cudaMemcpyAsync(D.stage_dev, val, (size_t)nnz * sb, cudaMemcpyHostToDevice, D.st));
+      CK(convert_rows_launch(s.val, eb, D.stage_dev, sb, nnz, 1, 1, D.st));
+    }
+  }
+  CK(cudaStreamSynchronize(D.st));
+  s.csr = true;
+  s.rows = rows;
+  s.cap = rows;
+  s.nnz = nnz;
+  s.elem_bytes = eb;
+  return 0;
+}
+
+int agd_clear(agd_handle *h) {
+  if (!h) return 1;
+  for (Dev &D : h->devs) {
+    std::lock_guard<std::mutex> g(*D.mu);
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaStreamSynchronize(D.st));
+    if (free_shard(h, D)) return 1;
+  }
+  h->d = 0;
+  return 0;
+}
+
+int64_t agd_rows(const agd_handle *h, int32_t dev) {
+  if (!h || dev < 0 || dev >= (int)h->devs.size()) return -1;
+  return h->devs[dev].sh.rows;
+}
+int32_t agd_dim(const agd_handle *h) { return h ? h->d : 0; }
+
+int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dtype, uint64_t seed, int32_t gradient) {
+  if (!h) return 1;
+  const int eb = dtype_bytes(store_dtype);
+  if (!eb) return fail(h, "store_dtype must be AGD_F32 or AGD_F64");
+  if (total_rows < 0) return fail(h, "negative row count");
+  if (agd_clear(h)) return 1;
+  if (set_dim(h, d)) return 1;
+  for (size_t i = 0; i < h->devs.size(); ++i) {
+    Dev &D = h->devs[i];
+    std::lock_guard<std::mutex> g(*D.mu);
+    const long long rank = h->first_rank + (long long)i, W = h->world;
+    const int64_t lo = (int64_t)(((__int128)rank * total_rows) / W), hi = (int64_t)(((__int128)(rank + 1) * total_rows) / W);
+    if (reserve_locked(h, D, hi - lo, d, store_dtype)) return 1;
+    if (ensure_vectors(h, D, d)) return 1;
+    CK(cudaSetDevice(D.ordinal));
+    CK(synth_dense_launch(D.sh.X, eb, seed, lo, hi - lo, d, D.st));
+    CK(synth_wtrue_launch(D.wtmp, seed, d, D.st));
+    CK(synth_labels_launch(D.sh.X, eb, D.wtmp, D.sh.labels, seed, gradient, lo, hi - lo, d, D.st));
+    D.sh.rows = hi - lo;
+  }
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  return 0;
+}
+
+int agd_get_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, void *X_out, double *labels_out) {
+  if (!h) return 1;
+  if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
+  Dev &D = h->devs[dev];
+  const Shard &s = D.sh;
+  if (s.csr) return fail(h, "agd_get_rows serves dense shards only");
+  if (row0 < 0 || rows < 0 || row0 + rows > s.rows) return fail(h, "row range out of bounds");
+  CK(cudaSetDevice(D.ordinal));
+  const size_t rb = (size_t)h->d * s.elem_bytes;
+  if (X_out && rows) CK(cudaMemcpyAsync(X_out, (const unsigned char *)s.X + (size_t)row0 * rb, (size_t)rows * rb, cudaMemcpyDeviceToHost, D.st));
+  if (labels_out && rows) CK(cudaMemcpyAsync(labels_out, s.labels + row0, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+  CK(cudaStreamSynchronize(D.st));
+  return 0;
+}
+
+int agd_synth_wtrue(agd_handle *h, uint64_t seed, int32_t d, double *w_out) {
+  if (!h) return 1;
+  Dev &D = h->devs[0];
+  CK(cudaSetDevice(D.ordinal));
+  double *tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)d * sizeof(double)));
+  CK(synth_wtrue_launch(tmp, seed, d, D.st));
+  CK(cudaMemcpyAsync(w_out, tmp, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+  CK(cudaStreamSynchronize(D.st));
+  cudaFree(tmp);
+  return 0;
+}
+
+int agd_set_option(agd_handle *h, const char *key, const char *value) {
+  if (!h || !key || !value) return 1;
+  if (!strcmp(key, "k1_variant")) {
+    if (!strcmp(value, "auto")) h->k1_variant = 0;
+    else if (!strcmp(value, "ring")) h->k1_variant = 1;
+    else if (!strcmp(value, "generic")) h->k1_variant = 2;
+    else return fail(h, "k1_variant must be auto|ring|generic");
+    return 0;
+  }
+  if (!strcmp(key, "ring_stages")) { h->ring_stages = atoi(value); return 0; }
+  if (!strcmp(key, "ring_rows")) { h->tune_rows = atoi(value); return 0; }
+  if (!strcmp(key, "ring_ctas")) { h->tune_ctas = atoi(value); return 0; }
+  return fail(h, "unknown option %s", key);
+}
+
+// ---------------------------------------------------------------- applySmooth with host buffers
+int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, double *grad, int64_t *count) {
+  if (check_ready(h)) return 1;
+  if (gradient < 0 || gradient > AGD_GRAD_LEAST_SQUARES_HALF) return fail(h, "unknown gradient %d", gradient);
+  const int32_t d = h->d;
+  for (Dev &D : h->devs) {
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaMemcpyAsync(D.wtmp, w, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, D.st));  // = broadcast, AGD.scala:193
+  }
+  h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
+  if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.wtmp; }, false)) return 1;
+  Dev &D0 = h->devs[0];
+  CK(cudaSetDevice(D0.ordinal));
+  std::vector<double> host((size_t)d + 2);
+  CK(cudaMemcpyAsync(host.data(), D0.acc, ((size_t)d + 2) * sizeof(double), cudaMemcpyDeviceToHost, D0.st));
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  const double cnt = host[(size_t)d + 1];
+  *loss = host[d] / cnt;                                    // AGD.scala:207
+  for (int32_t j = 0; j < d; ++j) grad[j] = host[j] / cnt;
+  if (count) *count = (int64_t)cnt;
+  return 0;
+}
+
+// ---------------------------------------------------------------- applyProjector with host buffers
+int agd_prox(agd_handle *h, int32_t updater, const double *w, const double *g, double step, double reg,
+             int32_t d, double *w_out, double *reg_val) {
+  if (!h) return 1;
+  if (updater < 0 || updater > AGD_UPD_L1) return fail(h, "unknown updater %d", updater);
+  if (d <= 0) return fail(h, "bad dimension");
+  Dev &D = h->devs[0];
+  CK(cudaSetDevice(D.ordinal));
+  double *buf = nullptr, *partials = nullptr;
+  CK(cudaMalloc(&buf, 3 * (size_t)d * sizeof(double)));
+  CK(cudaMalloc(&partials, (size_t)k3_blocks(d) * K3_NS * sizeof(double)));
+  CK(cudaMemcpyAsync(buf, w, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, D.st));
+  CK(cudaMemcpyAsync(buf + d, g, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, D.st));
+  K3ProxArgs a;
+  a.w = buf; a.g = buf + d; a.w_out = buf + 2 * (size_t)d; a.partials = partials; a.ticket = D.ticket;
+  a.scalars = D.scalars_dev; a.step = step; a.reg = reg; a.acc_tail = nullptr; a.d = d; a.updater = updater;
+  CK(k3_prox_launch(a, D.st));
+  CK(cudaMemcpyAsync(w_out, buf + 2 * (size_t)d, (size_t)d * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+  double sc[K3_NS];
+  if (read_scalars(h, sc)) return 1;
+  if (reg_val) *reg_val = reg_value(updater, reg, sc[2], sc[5]);
+  cudaFree(buf);
+  cudaFree(partials);
+  return 0;
+}
+
+// ---------------------------------------------------------------- AcceleratedGradientDescent.run
+int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out, double *loss_hist,
+            int32_t *n_hist, agd_stats *stats) {
+  if (check_ready(h)) return 1;
+  if (!p || !w0 || !w_out || !loss_hist || !n_hist) return fail(h, "NULL argument");
+  if (p->gradient < 0 || p->gradient > AGD_GRAD_LEAST_SQUARES_HALF) return fail(h, "unknown gradient %d", p->gradient);
+  if (p->updater < 0 || p->updater > AGD_UPD_L1) return fail(h, "unknown updater %d", p->updater);
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int32_t d = h->d;
+  const size_t vb = (size_t)d * sizeof(double);
+  const double INF = std::numeric_limits<double>::infinity();
+  agd_stats s;
+  memset(&s, 0, sizeof s);
+  h->launches = 0;
+  h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
+  const bool memoize = (p->flags & AGD_FLAG_MEMOIZE_FX) != 0;
+
+  for (Dev &D : h->devs) {                                                 // :224-225  x = w0 ; z = x
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaMemcpyAsync(D.x, w0, vb, cudaMemcpyHostToDevice, D.st));
+    CK(k3_copy2_launch(D.z, D.x, nullptr, nullptr, d, D.st));
+  }
+  h->launches += 1;
+  double theta = INF;                                                      // :226
+  int nh = 0;                                                              // :227
+  double f_y = 0.0;                                                        // :229
+  double L = p->L0;                                                        // :232
+  bool backtrack_simple = true;                                            // :234
+  const double backtrack_tol = 1e-10;                                      // :235
+  const double Lexact = p->Lexact, beta = p->beta;
+  double sc[K3_NS] = {0}, sg[K3_NS] = {0};
+
+  auto launch_all = [&](auto fn) -> int {
+    for (Dev &D : h->devs) {
+      CK(cudaSetDevice(D.ordinal));
+      CK(fn(D));
+    }
+    h->launches += 1;
+    return 0;
+  };
+
+  for (int nIter = 1; nIter <= p->num_iterations; ++nIter) {              // :237
+    if (launch_all([&](Dev &D) { return k3_copy2_launch(D.x_old, D.x, D.z_old, D.z, d, D.st); })) return 1;  // :241
+    const double L_old = L;                                                // :242
+    L = L * p->alpha;                                                      // :243
+    const double theta_old = theta;                                        // :244
+    bool nonterminating = false, have_fx = false;
+    double f_x = 0.0;
+    for (;;) {                                                             // :246
+      theta = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L / L_old) / (theta_old * theta_old)));  // :248
+      const double omt = 1.0 - theta;
+      if (launch_all([&](Dev &D) { return k3_combine_launch(D.y, D.x_old, omt, D.z_old, theta, d, D.st); })) return 1;  // :249
+      if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
+      s.passes++;
+      const double step = 1.0 / (theta * L);                               // :253
+      if (launch_all([&](Dev &D) {                                         // :254-255,263-264 fused
+            K3StepArgs a;
+            a.acc = D.acc; a.x_old = D.x_old; a.z_old = D.z_old; a.y = D.y; a.g_y = D.g_y; a.z = D.z; a.x = D.x;
+            a.partials = D.partials; a.ticket = D.ticket; a.scalars = D.scalars_dev;
+            a.theta = theta; a.one_minus_theta = omt; a.step = step; a.reg = p->reg_param; a.d = d; a.updater = p->updater;
+            return k3_step_launch(a, D.st);
+          })) return 1;
+      if (read_scalars(h, sc)) return 1;
+      f_y = sc[6] / sc[7];                                                 // :207
+      have_fx = false;
+      if (beta >= 1.0) break;                                              // :257
+      const double nxy = std::sqrt(sc[0]);
+      const double xy_sq = nxy * nxy;                                      // :264  math.pow(norm(xy), 2)
+      if (xy_sq == 0) break;                                               // :265
+      if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;  // :269
+      s.passes++;
+      if (launch_all([&](Dev &D) {
+            K3GxArgs a;
+            a.acc = D.acc; a.x = D.x; a.y = D.y; a.g_y = D.g_y; a.g_x = D.g_x; a.partials = D.partials;
+            a.ticket = D.ticket; a.scalars = D.scalars_dev + K3_NS; a.d = d;
+            return k3_gx_launch(a, D.st);
+          })) return 1;
+      {
+        Dev &D = h->devs[0];
+        CK(cudaSetDevice(D.ordinal));
+        CK(cudaMemcpyAsync(D.scalars_host + K3_NS, D.scalars_dev + K3_NS, K3_NS * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+        memcpy(sg, D.scalars_host + K3_NS, K3_NS * sizeof(double));
+      }
+      f_x = sg[6] / sg[7];
+      have_fx = true;
+      double localL;
+      if (backtrack_simple) {                                              // :272
+        const double q_x = f_y + sc[1] + 0.5 * L * xy_sq;                  // :273
+        localL = L + 2.0 * jmax(f_x - q_x, 0.0) / xy_sq;                   // :274
+        backtrack_simple = (std::fabs(f_y - f_x) >= backtrack_tol * jmax(std::fabs(f_x), std::fabs(f_y)));  // :275
+      } else {
+        localL = 2.0 * sg[0] / xy_sq;                                      // :278
+      }
+      if (localL <= L || L >= Lexact) break;                               // :281
+      if (!std::isinf(localL)) L = jmin(Lexact, localL);                   // :285-287
+      else localL = L;                                                     // :288-290
+      L = jmin(Lexact, jmax(localL, L / beta));                            // :292
+      s.backtracks++;
+      if (L != L) { nonterminating = true; break; }  // the reference never leaves :246-293 once L is NaN
+    }
+    if (!(memoize && have_fx)) {                                           // :304  (f_x, g_x) = applySmooth(x)
+      if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
+      s.passes++;
+      {
+        Dev &D = h->devs[0];
+        CK(cudaSetDevice(D.ordinal));
+        CK(cudaMemcpyAsync(D.scalars_host + K3_NS, D.acc + d, 2 * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+        CK(cudaStreamSynchronize(D.st));
+        f_x = D.scalars_host[K3_NS] / D.scalars_host[K3_NS + 1];
+      }
+    }
+    const double c_x = reg_value(p->updater, p->reg_param, sc[2], sc[5]);  // :305  applyProjector(x, g_x, 0.0)._1
+    loss_hist[nh++] = f_x + c_x;                                           // :306
+    s.iterations = nIter;
+    if (nonterminating) { s.stopped_nan = 1; s.nonterminating = 1; break; }
+    if (std::isnan(f_y) || std::isinf(f_y)) { s.stopped_nan = 1; break; }  // :309-312
+    const double norm_x = std::sqrt(sc[2]);                                // :315
+    const double norm_dx = std::sqrt(sc[3]);                               // :316
+    if (norm_dx == 0.0) { if (nIter > 1) { s.converged = 1; break; } }     // :317-321
+    if (norm_dx < p->convergence_tol * jmax(norm_x, 1)) { s.converged = 1; break; }  // :322-324
+    if (p->may_restart && sc[4] > 0.0) {                                   // :327
+      if (launch_all([&](Dev &D) { return k3_copy2_launch(D.z, D.x, nullptr, nullptr, d, D.st); })) return 1;  // :328
+      theta = INF;                                                         // :329
+      backtrack_simple = true;                                             // :330
+      s.restarts++;
+    }
+  }
+  {
+    Dev &D = h->devs[0];
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));    // :337
+  }
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  *n_hist = nh;
+  s.final_L = L;
+  s.final_theta = theta;
+  Dev &D0 = h->devs[0];
+  if (sum_events(h, D0.ev, D0.ev_used, &s.k1_ms_total)) return 1;
+  if (sum_events(h, D0.ev_ar, D0.ev_ar_used, &s.allreduce_ms_total)) return 1;
+  s.k1_launches = (int64_t)(D0.ev_used / 2);
+  s.gpu_launches = h->launches;
+  s.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  if (stats) *stats = s;
+  return 0;
+}
+
+// ---------------------------------------------------------------- GradientDescent.runMiniBatchSGD (fraction 1.0)
+int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_size, int32_t num_iterations,
+               double reg_param, const double *w0, double *w_out, double *loss_hist, int32_t *n_hist,
+               agd_stats *stats) {
+  if (check_ready(h)) return 1;
+  if (gradient < 0 || gradient > AGD_GRAD_LEAST_SQUARES_HALF) return fail(h, "unknown gradient %d", gradient);
+  if (updater < 0 || updater > AGD_UPD_L1) return fail(h, "unknown updater %d", updater);
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int32_t d = h->d;
+  const size_t vb = (size_t)d * sizeof(double);
+  agd_stats s;
+  memset(&s, 0, sizeof s);
+  h->launches = 0;
+  h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
+  double sc[K3_NS];
+  int64_t total_rows_local = 0;
+  for (Dev &D : h->devs) total_rows_local += D.sh.rows;
+  auto prox_all = [&](const double *acc_tail_sel, double step, bool from_acc) -> int {
+    for (Dev &D : h->devs) {
+      CK(cudaSetDevice(D.ordinal));
+      K3ProxArgs a;
+      a.w = D.x; a.g = from_acc ? D.acc : D.g_x; a.w_out = D.z; a.partials = D.partials; a.ticket = D.ticket;
+      a.scalars = D.scalars_dev; a.step = step; a.reg = reg_param; a.acc_tail = from_acc ? D.acc + d : nullptr;
+      a.d = d; a.updater = updater;
+      CK(k3_prox_launch(a, D.st));
+      CK(k3_copy2_launch(D.x, D.z, nullptr, nullptr, d, D.st));
+    }
+    (void)acc_tail_sel;
+    h->launches += 2;
+    return 0;
+  };
+  for (Dev &D : h->devs) {
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaMemcpyAsync(D.x, w0, vb, cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemsetAsync(D.g_x, 0, vb, D.st));
+  }
+  // regVal = updater.compute(weights, zeros, 0, 1, regParam)._2
+  if (prox_all(nullptr, 0.0, false)) return 1;
+  if (read_scalars(h, sc)) return 1;
+  double reg_val = reg_value(updater, reg_param, sc[2], sc[5]);
+  int nh = 0;
+  for (int i = 1; i <= num_iterations; ++i) {
+    if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
+    s.passes++;
+    const double this_step = step_size / std::sqrt((double)i);
+    if (prox_all(nullptr, this_step, true)) return 1;
+    if (read_scalars(h, sc)) return 1;
+    if (!(sc[7] > 0)) break;  // miniBatchSize == 0: the reference logs a warning and skips the update
+    loss_hist[nh++] = sc[6] / sc[7] + reg_val;
+    reg_val = reg_value(updater, reg_param, sc[2], sc[5]);
+    s.iterations = i;
+  }
+  {
+    Dev &D = h->devs[0];
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));
+  }
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  *n_hist = nh;
+  Dev &D0 = h->devs[0];
+  if (sum_events(h, D0.ev, D0.ev_used, &s.k1_ms_total)) return 1;
+  if (sum_events(h, D0.ev_ar, D0.ev_ar_used, &s.allreduce_ms_total)) return 1;
+  s.k1_launches = (int64_t)(D0.ev_used / 2);
+  s.gpu_launches = h->launches;
+  s.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  if (stats) *stats = s;
+  return 0;
+}
+
+}  // extern "C"

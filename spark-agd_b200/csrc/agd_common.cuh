@@ -1,0 +1,107 @@
+// agd_common.cuh -- shared declarations of the sm_100a hot-path kernels (internal, not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/agd_b200.h"
+
+namespace agd {
+
+// ---------------------------------------------------------------- K1: fused row-block gradient
+// Replaces the seqOp fold of AGD.scala:197-200 + Gradient.compute [mllib-1.3.0] over one shard.
+struct K1Args {
+  const void *X;          // shard, row-major, ld == d, element type float or double
+  const double *labels;   // rows (+ padding)
+  const double *w;        // d doubles (device)
+  double *slabs;          // [grid][d + 1]: per-block column sums of loss' * x, then the loss sum
+  int64_t rows;           // rows in the shard
+  int32_t d;
+  int32_t kind;           // AGD_GRAD_*
+  int32_t stages;         // smem ring depth
+  int32_t slab_stride;    // d + 1
+  int32_t tune_rows;      // 0 = default; rows per tile of the headline ring shape (4|8)
+  int32_t tune_ctas;      // 0 = default; resident CTAs per SM (1|2|3)
+};
+
+// launch helpers (k1_dense.cu); return the number of blocks that wrote a slab
+int k1_ring_supported(int32_t d, int elem_bytes);
+cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
+cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
+                              cudaStream_t st);
+int k1_max_blocks(int sm_count);
+// out[c] = sum_b slabs[b][c] for c <= d ; out[d+1] = rows   (fixed order => deterministic)
+cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st);
+
+// CSR variant (k1_csr.cu)
+struct K1CsrArgs {
+  const int64_t *rowptr;
+  const int32_t *idx;
+  const void *val;        // float or double
+  const double *labels;
+  const double *w;
+  double *gacc;           // d + 2 doubles, zeroed by the launch: gradient sum, loss sum, count
+  int64_t rows;
+  int32_t d;
+  int32_t kind;
+};
+cudaError_t k1_csr_launch(const K1CsrArgs &a, int elem_bytes, int sm_count, cudaStream_t st);
+
+// ---------------------------------------------------------------- K3: fused O(d) driver-side vector work
+// Replaces the breeze d-vector ops of AGD.scala:249,255,263-264,273,278,315-316,327, the
+// normalisation of :207 and Updater.compute [mllib-1.3.0] behind applyProjector (:214-222).
+enum { K3_NS = 8 };  // scalars produced per call
+struct K3StepArgs {
+  const double *acc;      // packed [grad_sum(d) | loss_sum | count] after the all-reduce
+  const double *x_old, *z_old, *y;
+  double *g_y, *z, *x;
+  double *partials;       // [blocks][K3_NS]
+  unsigned int *ticket;
+  double *scalars;        // [K3_NS]: S(x-y)^2, (x-y).g_y, S x^2, S (x-x_old)^2, g_y.(x-x_old), S|x|, loss_sum, count
+  double theta, one_minus_theta, step, reg;
+  int32_t d, updater;
+};
+cudaError_t k3_step_launch(const K3StepArgs &a, cudaStream_t st);
+struct K3GxArgs {
+  const double *acc;
+  const double *x, *y, *g_y;
+  double *g_x;
+  double *partials;
+  unsigned int *ticket;
+  double *scalars;        // [0] = (x-y).(g_x-g_y), [6] = loss_sum, [7] = count
+  int32_t d;
+};
+cudaError_t k3_gx_launch(const K3GxArgs &a, cudaStream_t st);
+// out = a*ca + b*cb (separate roundings, as breeze does at AGD.scala:249)
+cudaError_t k3_combine_launch(double *out, const double *a, double ca, const double *b, double cb, int32_t d,
+                              cudaStream_t st);
+// dst0 = src0 ; dst1 = src1 (either pair may be null)
+cudaError_t k3_copy2_launch(double *dst0, const double *src0, double *dst1, const double *src1, int32_t d,
+                            cudaStream_t st);
+// plain prox for agd_prox / the GD comparator: w_out = Updater.compute(w, g[/count], step, reg); scalars[2]=S w'^2, [5]=S|w'|
+struct K3ProxArgs {
+  const double *w, *g;
+  double *w_out;
+  double *partials;
+  unsigned int *ticket;
+  double *scalars;
+  double step, reg;
+  const double *acc_tail;   // optional {loss_sum, count} on the device: g is divided by count first
+                            // (count == 0 leaves w unchanged); scalars[6..7] receive the pair
+  int32_t d, updater;
+};
+cudaError_t k3_prox_launch(const K3ProxArgs &a, cudaStream_t st);
+int k3_blocks(int32_t d);
+
+// ---------------------------------------------------------------- K0: synthetic workload (harness)
+cudaError_t synth_dense_launch(void *X, int elem_bytes, uint64_t seed, int64_t row0, int64_t rows, int32_t d,
+                               cudaStream_t st);
+cudaError_t synth_wtrue_launch(double *w, uint64_t seed, int32_t d, cudaStream_t st);
+cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_true, double *labels, uint64_t seed,
+                                int kind, int64_t row0, int64_t rows, int32_t d, cudaStream_t st);
+
+// ---------------------------------------------------------------- load path
+// dst (store dtype, ld == d) <- src (src dtype, leading dimension ld), rows x d
+cudaError_t convert_rows_launch(void *dst, int dst_bytes, const void *src, int src_bytes, int64_t rows, int32_t d,
+                                int64_t ld, cudaStream_t st);
+
+}  // namespace agd

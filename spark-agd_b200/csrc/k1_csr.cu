@@ -1,0 +1,63 @@
+// k1_csr.cu -- K1 for SparseVector rows stored as CSR (sm_100a).
+//
+// Same contract as the dense kernel (seqOp fold of AGD.scala:197-200 with the sparse branches of
+// BLAS.dot / BLAS.axpy [mllib-1.3.0]): one warp per row, lanes stride the row's stored entries
+// (coalesced idx/val reads), w is gathered from the L2-resident fp64 vector, the margin is
+// warp-shuffle reduced, loss' is evaluated once per row, and mult * val is scattered into the
+// L2-resident fp64 gradient with RED.ADD.F64.  HBM traffic per pass = nnz*(4 + elem) + rows*16.
+// The scatter order is not fixed, so the gradient is reproducible only to fp64 rounding (~1e-16).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agd_common.cuh"
+#include "k1_device.cuh"
+
+namespace agd {
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) k1_csr_kernel(const K1CsrArgs a) {
+  __shared__ double red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (blockIdx.x * 256LL + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * 256LL) >> 5;
+  const T *val = reinterpret_cast<const T *>(a.val);
+  double lossacc = 0.0;
+  for (long long r = warp_global; r < a.rows; r += nwarps) {
+    const long long lo = a.rowptr[r], hi = a.rowptr[r + 1];
+    double m = 0.0;
+    for (long long k = lo + lane; k < hi; k += 32) m = fma((double)val[k], a.w[a.idx[k]], m);
+    for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(0xffffffffu, m, off);
+    double mult, loss;
+    loss_eval(a.kind, m, a.labels[r], mult, loss);
+    if (lane == 0) lossacc += loss;
+    if (mult != 0.0) {
+      for (long long k = lo + lane; k < hi; k += 32) atomicAdd(&a.gacc[a.idx[k]], mult * (double)val[k]);
+    }
+  }
+  for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+  if (lane == 0) red[warp] = lossacc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(&a.gacc[a.d], s);
+    if (blockIdx.x == 0) a.gacc[a.d + 1] = (double)a.rows;
+  }
+}
+
+}  // namespace
+
+cudaError_t k1_csr_launch(const K1CsrArgs &a, int elem_bytes, int sm_count, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(a.gacc, 0, ((size_t)a.d + 2) * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  long long grid = (a.rows + 7) / 8;
+  if (grid > 8LL * sm_count) grid = 8LL * sm_count;
+  if (grid < 1) grid = 1;
+  if (elem_bytes == 4) k1_csr_kernel<float><<<(unsigned)grid, 256, 0, st>>>(a);
+  else k1_csr_kernel<double><<<(unsigned)grid, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace agd

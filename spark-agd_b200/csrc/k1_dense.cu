@@ -1,0 +1,485 @@
+// k1_dense.cu -- K1: fused row-block gradient kernel for dense shards (sm_100a).
+//
+// One launch = the seqOp fold of applySmooth (AGD.scala:197-200) over one GPU's shard:
+//   m_i = x_i . w            (BLAS.dot inside Gradient.compute [mllib-1.3.0], call site AGD.scala:198)
+//   (mult_i, loss_i) = loss'(m_i, y_i)   (LogisticGradient / LeastSquaresGradient / HingeGradient)
+//   g += mult_i * x_i        (BLAS.axpy into cumGradient),  loss += loss_i
+// with X read from HBM exactly once.  X is stored fp32 or fp64; every product and every sum is fp64
+// (the driver loop branches on catastrophically cancelling fp64 quantities, AGD.scala:273-281,327).
+//
+// k1_ring_kernel (hot path, d*sizeof(T) a multiple of 16 and d <= 1024 vectors/row):
+//   * one producer lane streams 32 KB row tiles HBM -> shared memory with TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) through an S-stage full/empty ring, labels ride along;
+//   * w is staged once per CTA with the same TMA path, then lives in registers;
+//   * 256 consumer threads: thread t of a row group owns 128-bit column vectors {t, t+TPR, ...};
+//     it pulls its R x V vectors of the tile out of shared memory (LDS.128), converts once to fp64,
+//     forms R partial dots, warp-shuffle transpose-reduces them, one rotating "scalar" warp finishes
+//     the margins and evaluates loss', and the retained fp64 tile is then accumulated into the
+//     thread's private column sums (no atomics);
+//   * per-CTA column sums go to a slab; k1_reduce_kernel adds the slabs in fixed order.
+// k1_generic_kernel: any (rows, d), scalar loads, slab accumulators in global memory (L2-resident).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agd_common.cuh"
+#include "k1_device.cuh"
+
+namespace agd {
+
+namespace {
+
+constexpr int kConsumers = 256;
+constexpr int kMaxTileRows = 32;
+
+template <typename T> struct Elem;
+template <> struct Elem<float> { static constexpr int EPV = 4; };
+template <> struct Elem<double> { static constexpr int EPV = 2; };
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <typename T, int EPV>
+__device__ __forceinline__ void cvt_vec(const uint4 &raw, double (&out)[EPV]);
+template <>
+__device__ __forceinline__ void cvt_vec<float, 4>(const uint4 &raw, double (&out)[4]) {
+  out[0] = (double)__uint_as_float(raw.x);
+  out[1] = (double)__uint_as_float(raw.y);
+  out[2] = (double)__uint_as_float(raw.z);
+  out[3] = (double)__uint_as_float(raw.w);
+}
+template <>
+__device__ __forceinline__ void cvt_vec<double, 2>(const uint4 &raw, double (&out)[2]) {
+  out[0] = __hiloint2double((int)raw.y, (int)raw.x);
+  out[1] = __hiloint2double((int)raw.w, (int)raw.z);
+}
+
+__host__ __device__ inline uint32_t round_up_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+// shared-memory carve-up (identical on host and device)
+struct RingLayout {
+  uint32_t stage_stride, aux_off, partial_off, mult_off, red_off, cnt_off, bars_off, total;
+};
+__host__ __device__ inline RingLayout ring_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages) {
+  RingLayout L;
+  L.stage_stride = round_up_u32(tile_bytes, 128);
+  L.aux_off = L.stage_stride * stages;
+  L.partial_off = L.aux_off + round_up_u32(aux_bytes, 128);
+  L.mult_off = L.partial_off + kMaxTileRows * 8 * 8;
+  L.red_off = L.mult_off + kMaxTileRows * 8;
+  L.cnt_off = L.red_off + 16 * 8;
+  L.bars_off = L.cnt_off + round_up_u32(stages * 4, 8);
+  L.total = L.bars_off + (stages + 1) * 8;
+  return L;
+}
+
+// ---------------------------------------------------------------- the hot kernel
+template <typename T, int TPR, int V, int R, int MINB>
+__global__ void __launch_bounds__(kConsumers, MINB)
+k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uint32_t aux_bytes) {
+  constexpr int EPV = Elem<T>::EPV;
+  constexpr int NG = kConsumers / TPR;  // row groups per CTA
+  constexpr int WPG = TPR / 32;         // warps per row group
+  constexpr int TR = NG * R;            // rows per tile
+  constexpr int NW = kConsumers / 32;
+  static_assert(TR <= kMaxTileRows, "tile rows");
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const int S = a.stages;
+  const uint32_t row_bytes = (uint32_t)a.d * (uint32_t)sizeof(T);
+  const RingLayout L = ring_layout(TR * row_bytes, aux_bytes, S);
+  double *aux = reinterpret_cast<double *>(smem + L.aux_off);
+  double *partial = reinterpret_cast<double *>(smem + L.partial_off);  // [TR][8]
+  double *mult_s = reinterpret_cast<double *>(smem + L.mult_off);      // [TR]
+  double *red = reinterpret_cast<double *>(smem + L.red_off);
+  unsigned int *cnt = reinterpret_cast<unsigned int *>(smem + L.cnt_off);  // [S] warps done with the stage
+  const uint32_t bars = smem_u32(smem + L.bars_off);                   // full[s] = bars + 8*s ; wbar = bars + 8*S
+  const uint32_t wbar = bars + 8u * S;
+  const unsigned char *Xb = reinterpret_cast<const unsigned char *>(a.X);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // TMA fill of ring slot (kk % S) with this CTA's kk-th tile
+  auto fill = [&](long long kk) {
+    const long long tile = blockIdx.x + kk * (long long)gridDim.x;
+    if (tile >= ntiles) return;
+    const int s = (int)(kk % S);
+    const long long row0 = tile * TR;
+    const long long left = a.rows - row0;
+    const uint32_t rv = left < TR ? (uint32_t)left : (uint32_t)TR;
+    const uint32_t full = bars + 8u * s;
+    mbar_expect_tx(full, rv * row_bytes);
+    tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride), Xb + (size_t)row0 * row_bytes, rv * row_bytes, full);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bars + 8u * s, 1);
+      cnt[s] = 0u;
+    }
+    mbar_init(wbar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
+    tma_bulk_g2s(smem_u32(aux), a.w, (uint32_t)a.d * 8u, wbar);  // w: TMA-staged once per CTA
+    for (int s = 0; s < S; ++s) fill(s);
+  }
+  __syncthreads();
+
+  const int g = tid / TPR, t = tid % TPR, wig = t >> 5;
+  double wreg[V][EPV], acc[V][EPV];
+  mbar_wait(wbar, 0);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int vec = v * TPR + t;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+      wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
+      acc[v][e] = 0.0;
+    }
+  }
+  double lossacc = 0.0;
+  double ynext = 0.0;  // label of row (next tile, lane), prefetched one tile ahead by every warp
+  if (lane < TR) {
+    const long long r = (long long)blockIdx.x * TR + lane;
+    if (r < a.rows) ynext = a.labels[r];
+  }
+
+  long long k = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    const int s = (int)(k % S);
+    const uint32_t par = (uint32_t)((k / S) & 1);
+    const long long row0 = tile * TR;
+    const long long left = a.rows - row0;
+    const int rv = left < TR ? (int)left : TR;
+    const int sw = (int)(k & (NW - 1));  // this tile's scalar warp
+    const double ylab = ynext;
+    if (lane < TR) {
+      const long long r = (tile + gridDim.x) * TR + lane;
+      if (r < a.rows) ynext = a.labels[r];
+    }
+    mbar_wait(bars + 8u * s, par);
+
+    // pull this thread's R x V vectors out of the stage and widen them to fp64 once
+    double xd[R][V][EPV];
+    const unsigned char *stage = smem + (size_t)s * L.stage_stride;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int vec = v * TPR + t;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)vec * 16);
+        cvt_vec<T, EPV>(raw, xd[r][v]);
+      }
+    }
+    if (rv < TR) {  // ragged last tile: rows past the shard hold stale bytes
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (g * R + r >= rv) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) xd[r][v][e] = 0.0;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {  // the last warp to leave the stage refills it (no dedicated producer warp)
+      const unsigned int done = atomicAdd(&cnt[s], 1u);
+      if (done == NW - 1) {
+        cnt[s] = 0u;
+        fill(k + S);
+      }
+    }
+
+    // phase 1: R partial dots over this thread's columns
+    double p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) sacc = fma(xd[r][v][e], wreg[v][e], sacc);
+      p[r] = sacc;
+    }
+    const double tot = warp_rows_reduce<R>(p, lane);
+    if ((lane % (32 / R)) == 0) partial[(g * R + lane / (32 / R)) * 8 + wig] = tot;
+    __syncthreads();
+
+    if (warp == sw && lane < TR) {
+      double m = 0.0;
+#pragma unroll
+      for (int wi = 0; wi < WPG; ++wi) m += partial[lane * 8 + wi];
+      double mult, loss;
+      loss_eval(a.kind, m, ylab, mult, loss);
+      const bool valid = lane < rv;
+      mult_s[lane] = valid ? mult : 0.0;
+      lossacc += valid ? loss : 0.0;
+    }
+    __syncthreads();
+
+    // phase 2: g += mult_i * x_i on the retained fp64 tile
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double mu = mult_s[g * R + r];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[v][e] = fma(mu, xd[r][v][e], acc[v][e]);
+    }
+  }
+
+  // ---------------- per-CTA slab: column sums (row groups added in fixed order) and loss sum
+  double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
+  if (NG > 1) {
+    __syncthreads();  // aux (w staging) is free for reuse: every thread read it before the loop
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) aux[(size_t)g * (TPR * V * EPV) + (v * TPR + t) * EPV + e] = acc[v][e];
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          double sacc = 0.0;
+          for (int gg = 0; gg < NG; ++gg) sacc += aux[(size_t)gg * (TPR * V * EPV) + (v * TPR + t) * EPV + e];
+          acc[v][e] = sacc;
+        }
+    }
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int vec = v * TPR + t;
+      if (vec < nvec) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) slab[vec * EPV + e] = acc[v][e];
+      }
+    }
+  }
+  for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+  if (lane == 0) red[warp] = lossacc;
+  __syncthreads();
+  if (tid == 0) {
+    double sacc = 0.0;
+    for (int wi = 0; wi < NW; ++wi) sacc += red[wi];
+    slab[a.d] = sacc;
+  }
+}
+
+// ---------------------------------------------------------------- generic shapes
+template <typename T>
+__global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const long long ntiles) {
+  constexpr int R = 8;
+  __shared__ double part[R][8];
+  __shared__ double mult_s[R];
+  __shared__ double red[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const T *X = reinterpret_cast<const T *>(a.X);
+  double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
+  for (int c = tid; c <= a.d; c += 256) slab[c] = 0.0;
+  double lossacc = 0.0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * R;
+    const long long left = a.rows - row0;
+    const int rv = left < R ? (int)left : R;
+    double p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) p[r] = 0.0;
+    for (int c = tid; c < a.d; c += 256) {
+      const double wc = a.w[c];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r < rv) p[r] = fma((double)X[(size_t)(row0 + r) * a.d + c], wc, p[r]);
+    }
+    const double tot = warp_rows_reduce<R>(p, lane);
+    if ((lane & 3) == 0) part[lane >> 2][warp] = tot;
+    __syncthreads();
+    if (tid < R) {
+      double m = 0.0;
+#pragma unroll
+      for (int wi = 0; wi < 8; ++wi) m += part[tid][wi];
+      double mult = 0.0, loss = 0.0;
+      if (tid < rv) loss_eval(a.kind, m, a.labels[row0 + tid], mult, loss);
+      mult_s[tid] = mult;
+      lossacc += loss;
+    }
+    __syncthreads();
+    for (int c = tid; c < a.d; c += 256) {
+      double sacc = slab[c];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r < rv) sacc = fma(mult_s[r], (double)X[(size_t)(row0 + r) * a.d + c], sacc);
+      slab[c] = sacc;
+    }
+  }
+  for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+  if (lane == 0) red[warp] = lossacc;
+  __syncthreads();
+  if (tid == 0) {
+    double sacc = 0.0;
+    for (int wi = 0; wi < 8; ++wi) sacc += red[wi];
+    slab[a.d] = sacc;
+  }
+}
+
+// ---------------------------------------------------------------- slab reduction (combOp, AGD.scala:201-204)
+__global__ void __launch_bounds__(128) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int d,
+                                                        long long rows, double *__restrict__ out) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c <= d) {
+    const size_t stride = (size_t)d + 1;
+    double s0 = 0.0;
+    int b = 0;
+    for (; b + 8 <= blocks; b += 8) {
+      double v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = slabs[(size_t)(b + i) * stride + c];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s0 += v[i];
+    }
+    for (; b < blocks; ++b) s0 += slabs[(size_t)b * stride + c];
+    out[c] = s0;
+  }
+  if (c == 0) out[d + 1] = (double)rows;
+}
+
+struct RingShape { int tpr, v, r; };
+inline bool ring_shape(int32_t d, int elem_bytes, RingShape &sh, int &nvec) {
+  const int epv = 16 / elem_bytes;
+  if (d <= 0 || d % epv != 0) return false;
+  nvec = d / epv;
+  if (nvec <= 256) {
+    int tpr = 32;
+    while (tpr < nvec) tpr <<= 1;
+    const int ng = 256 / tpr;
+    int r = 8;
+    if (ng * r > kMaxTileRows) r = kMaxTileRows / ng;
+    sh = {tpr, 1, r};
+    return true;
+  }
+  if (nvec <= 512) { sh = {256, 2, 4}; return true; }
+  if (nvec <= 1024) { sh = {256, 4, 2}; return true; }
+  return false;
+}
+
+template <typename T, int TPR, int V, int R, int MINB>
+cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
+  constexpr int EPV = Elem<T>::EPV;
+  constexpr int NG = kConsumers / TPR;
+  constexpr int TR = NG * R;
+  K1Args a = a_in;
+  const uint32_t row_bytes = (uint32_t)a.d * sizeof(T);
+  const uint32_t tile_bytes = TR * row_bytes;
+  uint32_t aux_bytes = (uint32_t)a.d * 8u;
+  if (NG > 1) {
+    const uint32_t need = (uint32_t)NG * TPR * V * EPV * 8u;
+    if (need > aux_bytes) aux_bytes = need;
+  }
+  const uint32_t budget = (227u * 1024u - MINB * 1024u) / MINB;
+  int stages = a.stages > 0 ? a.stages : 4;
+  while (stages > 1 && ring_layout(tile_bytes, aux_bytes, stages).total > budget) --stages;
+  a.stages = stages;
+  const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages);
+  auto kern = k1_ring_kernel<T, TPR, V, R, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (a.rows + TR - 1) / TR;
+  long long grid = (long long)MINB * sm_count;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  *blocks_out = (int)grid;
+  kern<<<(unsigned)grid, kConsumers, L.total, st>>>(a, nvec, ntiles, aux_bytes);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
+                          cudaStream_t st) {
+  if (sh.v == 1) {
+    switch (sh.tpr) {
+      case 32: return launch_ring_inst<T, 32, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+      case 64: return launch_ring_inst<T, 64, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
+      case 128: return launch_ring_inst<T, 128, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
+      default: {
+        // tuning variants of the headline shape (rows per tile x resident CTAs per SM)
+        const int key = a.tune_rows * 10 + a.tune_ctas;
+        switch (key) {
+          case 81: return launch_ring_inst<T, 256, 1, 8, 1>(a, nvec, sm_count, blocks_out, st);
+          case 42: return launch_ring_inst<T, 256, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+          case 43: return launch_ring_inst<T, 256, 1, 4, 3>(a, nvec, sm_count, blocks_out, st);
+          default: return launch_ring_inst<T, 256, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
+        }
+      }
+    }
+  }
+  if (sh.v == 2) return launch_ring_inst<T, 256, 2, 4, 2>(a, nvec, sm_count, blocks_out, st);
+  return launch_ring_inst<T, 256, 4, 2, 2>(a, nvec, sm_count, blocks_out, st);
+}
+
+}  // namespace
+
+int k1_max_blocks(int sm_count) { return 3 * sm_count; }
+
+int k1_ring_supported(int32_t d, int elem_bytes) {
+  RingShape sh;
+  int nvec;
+  return ring_shape(d, elem_bytes, sh, nvec) ? 1 : 0;
+}
+
+cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
+  RingShape sh;
+  int nvec = 0;
+  if (!ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
+  if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
+  if (elem_bytes == 4) return launch_ring_t<float>(a, sh, nvec, sm_count, blocks_out, st);
+  return launch_ring_t<double>(a, sh, nvec, sm_count, blocks_out, st);
+}
+
+cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
+                              cudaStream_t st) {
+  if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
+  const long long ntiles = (a.rows + 7) / 8;
+  long long grid = k1_max_blocks(sm_count);
+  if (grid > max_blocks) grid = max_blocks;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  *blocks_out = (int)grid;
+  if (elem_bytes == 4) k1_generic_kernel<float><<<(unsigned)grid, 256, 0, st>>>(a, ntiles);
+  else k1_generic_kernel<double><<<(unsigned)grid, 256, 0, st>>>(a, ntiles);
+  return cudaGetLastError();
+}
+
+cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st) {
+  const int grid = (d + 1 + 127) / 128;
+  k1_reduce_kernel<<<grid, 128, 0, st>>>(slabs, blocks, d, (long long)rows, out);
+  return cudaGetLastError();
+}
+
+}  // namespace agd
