@@ -214,7 +214,10 @@ int reserve_locked(agd_handle *h, Dev &D, int64_t cap, int32_t d, int store_dtyp
   Shard &s = D.sh;
   if (s.csr) return fail(h, "device already holds a CSR shard");
   if (s.cap > 0 && s.elem_bytes != eb) return fail(h, "storage dtype mismatch with the resident shard");
-  if (cap <= s.cap) return 0;
+  if (cap <= s.cap) {
+    if (!s.elem_bytes) s.elem_bytes = eb;  // an empty shard still records its storage type
+    return 0;
+  }
   void *nx = nullptr;
   double *nl = nullptr;
   const size_t xbytes = (size_t)cap * d * eb + 64;

@@ -134,6 +134,25 @@ def test_strided_and_converted_load(agd, ctx, oracle):
     ds.close()
 
 
+@pytest.mark.parametrize("scale", [1e-8, 1.0, 30.0, 300.0, 700.0, 2000.0])
+@pytest.mark.parametrize("d", [1, 4])
+def test_logistic_extreme_margins(agd, ctx, oracle, scale, d):
+    """The device sigmoid/softplus (k1_device.cuh: table exp + shared reciprocal + fdlibm-style log)
+    against libm through the oracle, from vanishing to saturating margins (exp under/overflow)."""
+    rng = np.random.default_rng(77)
+    n = 8192
+    X = np.zeros((n, d))
+    X[:, 0] = np.linspace(-1.0, 1.0, n)
+    y = (rng.random(n) > 0.5).astype(np.float64)
+    w = np.zeros(d); w[0] = scale
+    ds = ctx.parallelize(y, X)
+    loss, g, _ = ds.smooth(agd.LogisticGradient(), w)
+    ref_loss, ref_g, _ = oracle.smooth(oracle.Data(y, X=X), "logistic", w)
+    np.testing.assert_allclose(loss, ref_loss, rtol=1e-13)
+    np.testing.assert_allclose(g[0], ref_g[0], rtol=1e-12)
+    ds.close()
+
+
 # ------------------------------------------------------------------ CSR rows (SparseVector)
 @pytest.mark.parametrize("grad", GRADS)
 @pytest.mark.parametrize("store", ["f32", "f64"])
@@ -245,6 +264,8 @@ def test_suite_T5_wide_rows(agd, ctx, oracle):                                  
 CASES = [
     # (n, d, grad, upd, reg, store, iters, kwargs)
     (1000, 100, "least_squares", "simple", 0.0, "f64", 30, {}),                    # BASELINE config 1
+    (1000, 100, "least_squares", "simple", 0.0, "f64", 12, {}),                    # same, before convergence noise
+    (1000, 100, "least_squares", "squared_l2", 0.1, "f64", 12, {}),
     (1000, 100, "least_squares", "squared_l2", 0.1, "f64", 30, {}),
     (1000, 100, "least_squares", "l1", 0.05, "f64", 30, {}),
     (20000, 1024, "logistic", "simple", 0.0, "f32", 10, {}),                       # config 2's shape, small n
@@ -273,14 +294,31 @@ def test_run_matches_oracle(agd, ctx, oracle, case, memoize):
                          reg_param=reg, L0=kw.get("L0", 1.0), Lexact=kw.get("Lexact", float("inf")),
                          beta=kw.get("beta", 0.5), alpha=kw.get("alpha", 0.9),
                          may_restart=kw.get("may_restart", True), partitions=2)
-    assert st.iterations == ref.iterations == len(hist) == len(ref.loss_history)
-    assert st.backtracks == ref.backtracks and st.restarts == ref.restarts
-    if not memoize:
-        assert st.passes == ref.passes
+    # The reference's trajectory is itself a function of Spark's partition count once f_x - q_x
+    # (AGD.scala:273-274) is rounding noise: re-run the oracle with other partitionings and demand
+    # identical branch decisions from the GPU only where the reference agrees with itself.
+    alts = [oracle.agd_run(oracle.Data(y, X=X), grad, upd, w0, convergence_tol=0.0, num_iterations=iters,
+                           reg_param=reg, L0=kw.get("L0", 1.0), Lexact=kw.get("Lexact", float("inf")),
+                           beta=kw.get("beta", 0.5), alpha=kw.get("alpha", 0.9),
+                           may_restart=kw.get("may_restart", True), partitions=P) for P in (1, 3, 8)]
+    sig = lambda r: (r.iterations, r.passes, r.backtracks, r.restarts)
+    stable = all(sig(a) == sig(ref) for a in alts)
+    assert st.iterations == len(hist)
+    if stable:
+        assert st.iterations == ref.iterations == len(ref.loss_history)
+        assert st.backtracks == ref.backtracks and st.restarts == ref.restarts
+        if not memoize:
+            assert st.passes == ref.passes
+        else:
+            assert st.passes <= ref.passes
+        np.testing.assert_allclose(hist, ref.loss_history, rtol=1e-11)
+        assert rel_err(w, ref.weights) < 1e-9
     else:
-        assert st.passes <= ref.passes
-    np.testing.assert_allclose(hist, ref.loss_history, rtol=1e-11)
-    assert rel_err(w, ref.weights) < 1e-9
+        spread = max(rel_err(a.weights, ref.weights) for a in alts)
+        k = min(len(hist), len(ref.loss_history))
+        assert k >= iters - 2
+        np.testing.assert_allclose(hist[:k], ref.loss_history[:k], rtol=1e-8)
+        assert rel_err(w, ref.weights) < max(10 * spread, 1e-9)
     assert rel_err(w, ref.weights) < 1e-5          # north_star's stated tolerance
     data.close()
 

@@ -24,7 +24,7 @@ eb = 4 if store == "f32" else 8
 bytes_pass = rows * d * eb + rows * 8
 w0 = np.zeros(d)
 out = []
-for (r, c, s) in [(8, 2, 0), (8, 2, 2), (8, 2, 3), (8, 1, 0), (8, 1, 6), (4, 2, 0), (4, 3, 0), (4, 3, 3)]:
+for (r, c, s) in [(8, 2, 0), (4, 3, 0)]:
     ds.set_option("ring_rows", r); ds.set_option("ring_ctas", c); ds.set_option("ring_stages", s)
     for grad in (S.LogisticGradient(), S.LeastSquaresGradient()):
         S.run_with_stats(ds, grad, S.SimpleUpdater(), 0.0, 2, 0.0, w0)  # warm-up
