@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json: AGD iters/sec & examples/sec on logistic
+10M x 1024 dense fp32 (configs[1]), 1/2/4/8 B200, next to the reference's path on the host cores.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one outer AGD iteration (AGD.scala:237-332) = 3 + 2b applySmooth passes over the shard
+with the reference's exact pass structure (flags = 0).  `value` = examples/sec = total rows x passes
+executed / time, shards resident in HBM when the timed region starts.  `e2e` is the same metric through
+the public call with HOST buffers: the shard upload from pinned host memory (what `.cache()` pays),
+the run, and the results coming back are all inside its timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "AGD examples/sec (rows x applySmooth passes / s), logistic 10M x 1024 dense fp32"
+SEED = 42
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(rows_local: int, d: int):
+    """dram bytes per K1 launch from the committed ncu capture, scaled to this launch's rows."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            t = json.load(f)
+        if t["d"] != d:
+            return None
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["rows"] * rows_local
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [ln.split(", ") for ts, ln in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or \
+               [ln.split(", ") for _, ln in self.lines]
+        rows = [r for r in rows if len(r) >= 9]
+        if not rows:
+            return None
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[5 + k].strip().lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_reference(rows: int, d: int, steps: int, warmup: int, X=None, y=None):
+    """Times the reference's CPU path (the oracle port: treeAggregate-shaped fp64 fold, one partition
+    per host thread) on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    cores = O.max_threads()
+    if X is None:
+        X = O.synth_dense_f32(SEED, 0, rows, d)
+        y = O.synth_labels(SEED, "logistic", 0, X, O.synth_wtrue(SEED, d))
+    D = O.Data(y, X=X)
+    w0 = np.zeros(d)
+    if warmup > 0:
+        O.agd_run(D, "logistic", "simple", w0, convergence_tol=0.0, num_iterations=warmup, partitions=cores, threads=cores)
+    t0 = time.perf_counter()
+    r = O.agd_run(D, "logistic", "simple", w0, convergence_tol=0.0, num_iterations=steps, partitions=cores, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": rows * r.passes / dt, "unit": "examples/s", "cores": cores, "kind": "port",
+            "sample": f"first {rows} rows of the workload x {steps} AGD iterations ({r.passes} passes), "
+                      f"{cores} partitions on {cores} threads, fp32 rows upcast to fp64",
+            "seconds": dt, "iters_per_sec": r.iterations / dt, "passes": r.passes, "rows": rows}
+
+
+def auto_cpu_rows(cores: int, d: int, rows_total: int) -> int:
+    # ~7 us per row-pass per thread at d = 1024 (sequential fp64 dot + axpy); aim at ~1 s per pass
+    est = int(1.4e5 * cores * 1024 / d)
+    return max(1000, min(rows_total, est, 4_000_000))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = O.max_threads()
+    rows = args.cpu_rows or auto_cpu_rows(cores, args.dim, args.rows)
+    steps = max(1, min(args.steps, 4))        # each step is a bounded sample; keep the arm within minutes
+    warm = 1 if args.warmup > 0 else 0
+    res = cpu_reference(rows, args.dim, steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "examples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": res["seconds"] / steps * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"logistic-loss AGD, {args.rows} x {args.dim} dense fp32 (BASELINE configs[1])",
+                   "sample_rows": rows, "note": "staple/spark-agd needs a JVM + Spark 1.3.0 (absent): this arm times the "
+                   "repo's C restatement of its treeAggregate path (oracle/), an optimistic stand-in"},
+        "iters_per_sec": res["iters_per_sec"],
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import spark_agd_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx = S.Context.from_torch_distributed(local)
+    else:
+        ctx = S.Context(devices=[local])
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node = --gpus"
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d = args.dim
+    total_rows = args.rows * (world if args.scaling == "weak" else 1)
+    grad, upd = S.LogisticGradient(), S.SimpleUpdater()
+    data = ctx.synthetic(total_rows, d, grad, seed=SEED, store="f32")     # K0: never timed
+    rows_local = data.local_rows(0)
+    w0 = np.zeros(d)
+
+    def run(ds, iters, memoize=False):
+        return S.run_with_stats(ds, grad, upd, 0.0, iters, 0.0, w0, memoize=memoize)
+
+    # ---- warm-up, then EXACTLY K timed steps, barrier + synchronize on both sides
+    barrier()
+    if args.warmup > 0:
+        run(data, args.warmup)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    w, hist, st = run(data, args.steps)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    dev_s = max_over_ranks(st.device_ms_total / 1e3)
+    value = total_rows * st.passes / dev_s
+    # the bit-identical memoised pass structure (AGD_FLAG_MEMOIZE_FX), reported beside the headline
+    barrier()
+    _, _, st_m = run(data, args.steps, memoize=True)
+    dev_s_m = max_over_ranks(st_m.device_ms_total / 1e3)
+
+    # ---- roofline of the dominant kernel (K1), CUDA events on its own stream inside the timed region
+    peak, peak_src = peaks()
+    k1_ms = st.k1_ms_total / max(st.k1_launches, 1)
+    alg_bytes = rows_local * (d * 4 + 8)          # fp32 row + fp64 label, per launch
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k1_ring_kernel<float,256,1,8,2>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows_local, d),
+                "peak_source": peak_src, "bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
+                "k1_share_of_step": st.k1_ms_total / st.device_ms_total}
+
+    # ---- e2e: public call with HOST buffers; shard upload + run + results inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(S, ctx, data, rows_local, total_rows, d, args, run, barrier, max_over_ranks, world)
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N = 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = O.max_threads()
+        n_s = min(args.cpu_rows or auto_cpu_rows(cores, d, total_rows), rows_local)
+        Xs, ys = data.get_rows(0, 0, n_s)           # the very rows the GPU holds
+        res = cpu_reference(n_s, d, 2, 0, Xs, ys)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"logistic-loss AGD, {total_rows} x {d} dense fp32 (BASELINE configs[1]), "
+                                   f"SimpleUpdater, w0 = 0, convergenceTol 0, defaults L0=1 beta=.5 alpha=.9 restart",
+                       "rows": total_rows, "d": d, "store": "f32", "rows_per_gpu": rows_local,
+                       "parallelism": f"row shards x{world}, one all-reduce of d+2 fp64 per pass",
+                       "l2": "inputs larger than L2: every pass streams the whole shard "
+                             f"({alg_bytes / 1e9:.2f} GB) from HBM"},
+            "iters_per_sec": st.iterations / dev_s, "passes": st.passes, "passes_per_iter": st.passes / st.iterations,
+            "backtracks": st.backtracks, "restarts": st.restarts, "final_loss": float(hist[-1]),
+            "memoized": {"iters_per_sec": st_m.iterations / dev_s_m, "passes_per_iter": st_m.passes / st_m.iterations,
+                         "examples_per_sec": total_rows * st_m.passes / dev_s_m,
+                         "note": "AGD_FLAG_MEMOIZE_FX: same weights and history bit for bit, fewer passes"},
+            "allreduce_ms_per_pass": st.allreduce_ms_total / max(st.collective_calls, 1),
+            "host_wall_s": st.seconds_total, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(st.gpu_launches), "collective_calls": int(st.collective_calls), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    data.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(S, ctx, data, rows_local, total_rows, d, args, run, barrier, max_over_ranks, world):
+    import torch
+    shard_bytes = rows_local * d * 4
+    pinned = True
+    try:
+        hostX = torch.empty((rows_local, d), dtype=torch.float32, pin_memory=True)
+        hosty = torch.empty((rows_local,), dtype=torch.float64, pin_memory=True)
+    except RuntimeError:
+        pinned = False
+        hostX = torch.empty((rows_local, d), dtype=torch.float32)
+        hosty = torch.empty((rows_local,), dtype=torch.float64)
+    Xn, yn = hostX.numpy(), hosty.numpy()
+    chunk = max(1, (256 << 20) // (d * 4))
+    for r0 in range(0, rows_local, chunk):               # stage the caller's host copy (not timed)
+        rc = min(chunk, rows_local - r0)
+        xs, ys = data.get_rows(0, r0, rc)
+        Xn[r0:r0 + rc] = xs
+        yn[r0:r0 + rc] = ys
+    barrier()
+    t0 = time.perf_counter()
+    ds = S.DeviceDataset(ctx)                            # the call a user makes: load host rows, optimise
+    ds.load_dense(yn, Xn, store="f32")
+    w, hist, st = run(ds, args.steps)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    ds.close()
+    return {"value": total_rows * st.passes / dt, "unit": "examples/s", "seconds": dt,
+            "h2d_bytes_per_step": (shard_bytes + rows_local * 8 + d * 8) / args.steps,
+            "d2h_bytes_per_step": (d * 8 + len(hist) * 8) / args.steps + st.passes / args.steps * 64,
+            "iters_per_sec": st.iterations / dt, "pinned_host": pinned,
+            "what": f"agd_load_dense of the {shard_bytes / 1e9:.2f} GB fp32 shard from {'pinned' if pinned else 'pageable'} "
+                    f"host memory + agd_run({args.steps} iterations) + weights/history back, per rank, wall clock max over ranks"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -74,8 +74,10 @@ typedef struct {
   double seconds_total;   /* host wall time inside agd_run */
   double k1_ms_total;     /* CUDA-event time of the gradient kernel (device 0), all passes */
   int64_t k1_launches;    /* launches of the gradient kernel per device */
-  int64_t gpu_launches;   /* all kernel launches issued by this call, per device */
+  int64_t gpu_launches;   /* this library's own kernel launches issued by the call, per device */
   double allreduce_ms_total; /* CUDA-event time of the all-reduce (0 when world == 1) */
+  double device_ms_total;    /* CUDA events on device 0's stream around the whole call */
+  int64_t collective_calls;  /* all-reduces enqueued per device (library kernels, not counted in gpu_launches) */
 } agd_stats;
 
 /* ---- lifecycle ---- */

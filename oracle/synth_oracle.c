@@ -53,6 +53,9 @@ static const double kScale64 = 1.7320508075688772 / 65536.0; /* sqrt(3)/65536 */
 void oracle_synth_dense_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, float *X) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const float scale = (float)kScale64;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int64_t r = 0; r < rows; ++r) {
     const uint64_t i = (uint64_t)(row0 + r);
     float *x = X + r * (int64_t)d;
@@ -78,6 +81,9 @@ void oracle_synth_wtrue(uint64_t seed, int32_t d, double *w) {
 void oracle_synth_labels(uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, const float *X,
                          const double *w_true, double *labels) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
   for (int64_t r = 0; r < rows; ++r) {
     const uint64_t i = (uint64_t)(row0 + r);
     const float *x = X + r * (int64_t)d;

@@ -28,7 +28,8 @@ class Stats(C.Structure):
                 ("restarts", C.c_int32), ("converged", C.c_int32), ("stopped_nan", C.c_int32),
                 ("nonterminating", C.c_int32), ("reserved0", C.c_int32), ("final_L", C.c_double),
                 ("final_theta", C.c_double), ("seconds_total", C.c_double), ("k1_ms_total", C.c_double),
-                ("k1_launches", C.c_int64), ("gpu_launches", C.c_int64), ("allreduce_ms_total", C.c_double)]
+                ("k1_launches", C.c_int64), ("gpu_launches", C.c_int64), ("allreduce_ms_total", C.c_double),
+                ("device_ms_total", C.c_double), ("collective_calls", C.c_int64)]
 
 
 def _sources():

@@ -112,6 +112,8 @@ struct agd_handle {
   std::string err;
   std::mutex mu;
   int64_t launches = 0;  // per device, current call
+  int64_t collectives = 0;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 };
 
 namespace {
@@ -307,7 +309,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     for (Dev &D : h->devs) CKN(N.AllReduce(D.acc, D.acc, (size_t)d + 2, ncclDouble, ncclSum, D.comm, D.st));
     CKN(N.GroupEnd());
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
-    h->launches += 1;
+    h->collectives += 1;
   }
   return 0;
 }
@@ -337,6 +339,35 @@ int check_ready(agd_handle *h) {
   if (h->d <= 0) return fail(h, "no shard loaded (call agd_load_dense / agd_load_csr / agd_generate first)");
   for (Dev &D : h->devs)
     if (ensure_vectors(h, D, h->d)) return 1;
+  return 0;
+}
+
+int call_begin(agd_handle *h) {
+  Dev &D = h->devs[0];
+  CK(cudaSetDevice(D.ordinal));
+  if (!h->ev_begin) { CK(cudaEventCreate(&h->ev_begin)); CK(cudaEventCreate(&h->ev_end)); }
+  h->launches = 0;
+  h->collectives = 0;
+  D.ev_used = D.ev_ar_used = 0;
+  CK(cudaEventRecord(h->ev_begin, D.st));
+  return 0;
+}
+
+// all devices drained; fills the timing part of the stats
+int call_end(agd_handle *h, agd_stats &s, std::chrono::steady_clock::time_point t_begin) {
+  Dev &D0 = h->devs[0];
+  CK(cudaSetDevice(D0.ordinal));
+  CK(cudaEventRecord(h->ev_end, D0.st));
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev_begin, h->ev_end));
+  s.device_ms_total = ms;
+  if (sum_events(h, D0.ev, D0.ev_used, &s.k1_ms_total)) return 1;
+  if (sum_events(h, D0.ev_ar, D0.ev_ar_used, &s.allreduce_ms_total)) return 1;
+  s.k1_launches = (int64_t)(D0.ev_used / 2);
+  s.gpu_launches = h->launches;
+  s.collective_calls = h->collectives;
+  s.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   return 0;
 }
 
@@ -443,6 +474,7 @@ int agd_destroy(agd_handle *h) {
     if (D.stage_dev) cudaFree(D.stage_dev);
     for (cudaEvent_t e : D.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : D.ev_ar) cudaEventDestroy(e);
+    if (&D == &h->devs[0] && h->ev_begin) { cudaEventDestroy(h->ev_begin); cudaEventDestroy(h->ev_end); }
     if (D.st) cudaStreamDestroy(D.st);
     delete D.mu;
   }
@@ -678,6 +710,7 @@ int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, d
     CK(cudaMemcpyAsync(D.wtmp, w, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, D.st));  // = broadcast, AGD.scala:193
   }
   h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
+  h->launches = h->collectives = 0;
   if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.wtmp; }, false)) return 1;
   Dev &D0 = h->devs[0];
   CK(cudaSetDevice(D0.ordinal));
@@ -730,8 +763,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   const double INF = std::numeric_limits<double>::infinity();
   agd_stats s;
   memset(&s, 0, sizeof s);
-  h->launches = 0;
-  h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
+  if (call_begin(h)) return 1;
   const bool memoize = (p->flags & AGD_FLAG_MEMOIZE_FX) != 0;
 
   for (Dev &D : h->devs) {                                                 // :224-225  x = w0 ; z = x
@@ -850,16 +882,10 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     CK(cudaSetDevice(D.ordinal));
     CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));    // :337
   }
-  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  if (call_end(h, s, t_begin)) return 1;
   *n_hist = nh;
   s.final_L = L;
   s.final_theta = theta;
-  Dev &D0 = h->devs[0];
-  if (sum_events(h, D0.ev, D0.ev_used, &s.k1_ms_total)) return 1;
-  if (sum_events(h, D0.ev_ar, D0.ev_ar_used, &s.allreduce_ms_total)) return 1;
-  s.k1_launches = (int64_t)(D0.ev_used / 2);
-  s.gpu_launches = h->launches;
-  s.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   if (stats) *stats = s;
   return 0;
 }
@@ -876,8 +902,7 @@ int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_siz
   const size_t vb = (size_t)d * sizeof(double);
   agd_stats s;
   memset(&s, 0, sizeof s);
-  h->launches = 0;
-  h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
+  if (call_begin(h)) return 1;
   double sc[K3_NS];
   int64_t total_rows_local = 0;
   for (Dev &D : h->devs) total_rows_local += D.sh.rows;
@@ -921,14 +946,8 @@ int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_siz
     CK(cudaSetDevice(D.ordinal));
     CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));
   }
-  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  if (call_end(h, s, t_begin)) return 1;
   *n_hist = nh;
-  Dev &D0 = h->devs[0];
-  if (sum_events(h, D0.ev, D0.ev_used, &s.k1_ms_total)) return 1;
-  if (sum_events(h, D0.ev_ar, D0.ev_ar_used, &s.allreduce_ms_total)) return 1;
-  s.k1_launches = (int64_t)(D0.ev_used / 2);
-  s.gpu_launches = h->launches;
-  s.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   if (stats) *stats = s;
   return 0;
 }
