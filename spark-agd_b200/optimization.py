@@ -165,6 +165,12 @@ class DeviceDataset:
     def cache(self) -> "DeviceDataset":  # shards are always resident; kept for call-site parity
         return self
 
+    def unpersist(self) -> "DeviceDataset":
+        """Drops every shard but keeps the context (devices, communicator) for the next load."""
+        N.check(N.lib().agd_clear(self.h), self.h)
+        self.total_rows = 0
+        return self
+
     def load_dense(self, labels, X, store: str = "f64"):
         labels = np.ascontiguousarray(labels, dtype=np.float64)
         X = np.asarray(X)
