@@ -106,9 +106,10 @@ struct agd_handle {
   int32_t d = 0;
   int world = 1, first_rank = 0;
   bool comm_ready = false;
-  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic
+  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised
   int ring_stages = 0;
   int tune_rows = 0, tune_ctas = 0;
+  int k1_diag = 0;
   std::string err;
   std::mutex mu;
   int64_t launches = 0;  // per device, current call
@@ -279,12 +280,13 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
       continue;
     }
     K1Args a;
-    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.rows = s.rows; a.d = d; a.kind = kind;
+    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
     a.stages = h->ring_stages; a.slab_stride = d + 1; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     bool ring = k1_ring_supported(d, eb) != 0;
     if (h->k1_variant == 2) ring = false;
-    if (h->k1_variant == 1 && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
+    const bool ws = ring && h->k1_variant == 3;
+    if ((h->k1_variant == 1 || h->k1_variant == 3) && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
     int max_blocks = k1_max_blocks(D.sm_count);
     if (!ring) {  // generic: bound the slab memory for very wide rows
       const long long lim = (32LL << 20) / ((long long)d + 1);
@@ -294,7 +296,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     a.slabs = D.slabs;
     int blocks = 0;
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-    if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
+    if (ws) CK(k1_ws_launch(a, eb, D.sm_count, &blocks, D.st));
+    else if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
     else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
     CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, D.st));
@@ -691,10 +694,12 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
     if (!strcmp(value, "auto")) h->k1_variant = 0;
     else if (!strcmp(value, "ring")) h->k1_variant = 1;
     else if (!strcmp(value, "generic")) h->k1_variant = 2;
-    else return fail(h, "k1_variant must be auto|ring|generic");
+    else if (!strcmp(value, "ws")) h->k1_variant = 3;
+    else return fail(h, "k1_variant must be auto|ring|generic|ws");
     return 0;
   }
   if (!strcmp(key, "ring_stages")) { h->ring_stages = atoi(value); return 0; }
+  if (!strcmp(key, "k1_diag")) { h->k1_diag = atoi(value); return 0; }
   if (!strcmp(key, "ring_rows")) { h->tune_rows = atoi(value); return 0; }
   if (!strcmp(key, "ring_ctas")) { h->tune_ctas = atoi(value); return 0; }
   return fail(h, "unknown option %s", key);

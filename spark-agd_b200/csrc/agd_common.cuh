@@ -26,6 +26,7 @@ struct K1Args {
 // launch helpers (k1_dense.cu); return the number of blocks that wrote a slab
 int k1_ring_supported(int32_t d, int elem_bytes);
 cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
+cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
 cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
                               cudaStream_t st);
 int k1_max_blocks(int sm_count);

@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "agd_common.cuh"
 #include "k1_device.cuh"
 
@@ -100,20 +102,20 @@ __host__ __device__ inline RingLayout ring_layout(uint32_t tile_bytes, uint32_t 
 }
 
 // ---------------------------------------------------------------- the hot kernel
-template <typename T, int TPR, int V, int R, int MINB>
-__global__ void __launch_bounds__(kConsumers, MINB)
+template <typename T, int NT, int TPR, int V, int R, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uint32_t aux_bytes) {
   constexpr int EPV = Elem<T>::EPV;
-  constexpr int NG = kConsumers / TPR;  // row groups per CTA
+  constexpr int NG = NT / TPR;          // row groups per CTA
   constexpr int WPG = TPR / 32;         // warps per row group
   constexpr int TR = NG * R;            // rows per tile
-  constexpr int NW = kConsumers / 32;
-  static_assert(TR <= kMaxTileRows, "tile rows");
+  constexpr int NW = NT / 32;
+  static_assert(TR <= kMaxTileRows && TR % 2 == 0 && (NW & (NW - 1)) == 0, "tile rows / warps");
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int S = a.stages;
   const uint32_t row_bytes = (uint32_t)a.d * (uint32_t)sizeof(T);
-  const RingLayout L = ring_layout(TR * row_bytes, aux_bytes, S);
+  const RingLayout L = ring_layout(TR * row_bytes + kMaxTileRows * 8, aux_bytes, S);  // rows, then their labels
   double *aux = reinterpret_cast<double *>(smem + L.aux_off);
   double *partial = reinterpret_cast<double *>(smem + L.partial_off);  // [TR][8]
   double *mult_s = reinterpret_cast<double *>(smem + L.mult_off);      // [TR]
@@ -125,16 +127,17 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // TMA fill of ring slot (kk % S) with this CTA's kk-th tile
-  auto fill = [&](long long kk) {
+  auto fill = [&](long long kk, int s) {
     const long long tile = blockIdx.x + kk * (long long)gridDim.x;
     if (tile >= ntiles) return;
-    const int s = (int)(kk % S);
     const long long row0 = tile * TR;
     const long long left = a.rows - row0;
     const uint32_t rv = left < TR ? (uint32_t)left : (uint32_t)TR;
     const uint32_t full = bars + 8u * s;
-    mbar_expect_tx(full, rv * row_bytes);
+    const uint32_t lbytes = round_up_u32(rv * 8u, 16u);  // label arrays are padded, row0 is even
+    mbar_expect_tx(full, rv * row_bytes + lbytes);
     tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride), Xb + (size_t)row0 * row_bytes, rv * row_bytes, full);
+    tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride + TR * row_bytes), a.labels + row0, lbytes, full);
   };
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -145,44 +148,44 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     mbar_fence_init();
     mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
     tma_bulk_g2s(smem_u32(aux), a.w, (uint32_t)a.d * 8u, wbar);  // w: TMA-staged once per CTA
-    for (int s = 0; s < S; ++s) fill(s);
+    for (int s = 0; s < S; ++s) fill(s, s);
   }
   __syncthreads();
 
   const int g = tid / TPR, t = tid % TPR, wig = t >> 5;
-  double wreg[V][EPV], acc[V][EPV];
-  mbar_wait(wbar, 0);
+  double acc[V][EPV], acc2[V][EPV];
+  mbar_wait(wbar, 0);  // w is in shared memory; it is re-read per tile so that it is not live across phase 2
 #pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const int vec = v * TPR + t;
+  for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int e = 0; e < EPV; ++e) {
-      wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
       acc[v][e] = 0.0;
+      acc2[v][e] = 0.0;
     }
-  }
   double lossacc = 0.0;
-  double ynext = 0.0;  // label of row (next tile, lane), prefetched one tile ahead by every warp
-  if (lane < TR) {
-    const long long r = (long long)blockIdx.x * TR + lane;
-    if (r < a.rows) ynext = a.labels[r];
-  }
 
-  long long k = 0;
+  int k = 0, s = -1;
+  uint32_t par = 1;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-    const int s = (int)(k % S);
-    const uint32_t par = (uint32_t)((k / S) & 1);
+    if (++s == S) s = 0;          // ring slot and its mbarrier phase, kept incrementally
+    if (s == 0) par ^= 1u;
     const long long row0 = tile * TR;
     const long long left = a.rows - row0;
     const int rv = left < TR ? (int)left : TR;
-    const int sw = (int)(k & (NW - 1));  // this tile's scalar warp
-    const double ylab = ynext;
-    if (lane < TR) {
-      const long long r = (tile + gridDim.x) * TR + lane;
-      if (r < a.rows) ynext = a.labels[r];
-    }
+    const int sw = k & (NW - 1);  // this tile's scalar warp
     mbar_wait(bars + 8u * s, par);
+    // labels ride in the stage: no warp ever waits on a global load inside the loop
+    double ylab = 0.0;
+    if (warp == sw && lane < TR)
+      ylab = *reinterpret_cast<const double *>(smem + (size_t)s * L.stage_stride + TR * row_bytes + lane * 8);
 
+    double wreg[V][EPV];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int vec = v * TPR + t;
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
+    }
     // pull this thread's R x V vectors out of the stage and widen them to fp64 once
     double xd[R][V][EPV];
     const unsigned char *stage = smem + (size_t)s * L.stage_stride;
@@ -211,8 +214,20 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       const unsigned int done = atomicAdd(&cnt[s], 1u);
       if (done == NW - 1) {
         cnt[s] = 0u;
-        fill(k + S);
+        fill((long long)k + S, s);
       }
+    }
+
+    if (a.kind == 100 || a.kind == 101) {  // diagnostics (option k1_diag): 100 = stream + widen only, 101 = + phase 1, no barriers
+      double sacc = 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) sacc = (a.kind == 100) ? sacc + xd[r][v][e] : fma(xd[r][v][e], wreg[v][e], sacc);
+      acc[0][0] += sacc;
+      continue;
     }
 
     // phase 1: R partial dots over this thread's columns
@@ -231,9 +246,10 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     __syncthreads();
 
     if (warp == sw && lane < TR) {
-      double m = 0.0;
+      double pw[8];
 #pragma unroll
-      for (int wi = 0; wi < WPG; ++wi) m += partial[lane * 8 + wi];
+      for (int wi = 0; wi < 8; ++wi) pw[wi] = (wi < WPG) ? partial[lane * 8 + wi] : 0.0;
+      const double m = ((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7]));
       double mult, loss;
       loss_eval(a.kind, m, ylab, mult, loss);
       const bool valid = lane < rv;
@@ -243,15 +259,24 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     __syncthreads();
 
     // phase 2: g += mult_i * x_i on the retained fp64 tile
+    double mu[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mu[r] = mult_s[g * R + r];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const double mu = mult_s[g * R + r];
 #pragma unroll
       for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[v][e] = fma(mu, xd[r][v][e], acc[v][e]);
+        for (int e = 0; e < EPV; ++e) {
+          if (R > 1 && (r & 1)) acc2[v][e] = fma(mu[r], xd[r][v][e], acc2[v][e]);
+          else acc[v][e] = fma(mu[r], xd[r][v][e], acc[v][e]);
+        }
     }
   }
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) acc[v][e] += acc2[v][e];
 
   // ---------------- per-CTA slab: column sums (row groups added in fixed order) and loss sum
   double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
@@ -290,6 +315,254 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     double sacc = 0.0;
     for (int wi = 0; wi < NW; ++wi) sacc += red[wi];
     slab[a.d] = sacc;
+  }
+}
+
+// ---------------------------------------------------------------- warp-specialised hot kernel
+// One CTA per SM: 16 consumer warps, 1 scalar warp, 1 TMA producer warp.  Consumers never meet a
+// CTA-wide barrier: step j publishes its partial dots and *arrives* on a named barrier; the scalar warp
+// turns them into loss' values while the consumers already pull and reduce step j+1; only then do the
+// consumers *sync* on the (normally long completed) result and apply phase 2 to the retained step j.
+//   named barriers: P[b] = 1 + b (512 consumer arrivals + scalar warp sync),
+//                   M[b] = 3 + b (scalar warp arrival + 512 consumer syncs),  5 = consumers only.
+constexpr int kWsConsumers = 512;
+constexpr int kWsThreads = kWsConsumers + 128;  // + one auxiliary warpgroup (scalar, producer, 2 idle)
+constexpr int kWsConsumerRegs = 104, kWsAuxRegs = 64;  // inc draws from what dec released: 128*(96-64) = 512*(104-96)
+
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+struct WsLayout {
+  uint32_t stage_stride, aux_off, partial_off, mult_off, bars_off, total;
+};
+__host__ __device__ inline WsLayout ws_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages) {
+  WsLayout L;
+  L.stage_stride = round_up_u32(tile_bytes, 128);
+  L.aux_off = L.stage_stride * stages;
+  L.partial_off = L.aux_off + round_up_u32(aux_bytes, 128);
+  L.mult_off = L.partial_off + 2 * kMaxTileRows * 8 * 8;
+  L.bars_off = L.mult_off + 2 * kMaxTileRows * 8;
+  L.total = L.bars_off + (2 * stages + 1) * 8;
+  return L;
+}
+
+template <typename T, int TPR, int V, int R>
+__global__ void __launch_bounds__(kWsThreads, 1)
+k1_ws_kernel(const K1Args a, const int nvec, const long long ntiles, const uint32_t aux_bytes) {
+  constexpr int EPV = Elem<T>::EPV;
+  constexpr int NG = kWsConsumers / TPR;
+  constexpr int WPG = TPR / 32;
+  constexpr int TR = NG * R;  // rows per step
+  constexpr int NCW = kWsConsumers / 32;
+  static_assert(TR <= kMaxTileRows && WPG <= 8, "step rows");
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  const int S = a.stages;
+  const uint32_t row_bytes = (uint32_t)a.d * (uint32_t)sizeof(T);
+  const WsLayout L = ws_layout(TR * row_bytes, aux_bytes, S);
+  double *aux = reinterpret_cast<double *>(smem + L.aux_off);
+  double *partial = reinterpret_cast<double *>(smem + L.partial_off);  // [2][TR][8]
+  double *mult_s = reinterpret_cast<double *>(smem + L.mult_off);      // [2][TR]
+  const uint32_t bars = smem_u32(smem + L.bars_off);  // full[s] = +8s ; empty[s] = +8(S+s) ; wbar = +16S
+  const uint32_t wbar = bars + 16u * S;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long my_steps = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bars + 8u * s, 1);
+      mbar_init(bars + 8u * (S + s), NCW);
+    }
+    mbar_init(wbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // Register re-partition (setmaxnreg): the auxiliary warpgroup gives registers back, the consumers take
+  // them.  Each role's code sits wholly inside its own branch so that ptxas allocates per role.
+  if (warp >= NCW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsAuxRegs));
+   if (warp == NCW + 1) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
+      tma_bulk_g2s(smem_u32(aux), a.w, (uint32_t)a.d * 8u, wbar);
+      const unsigned char *Xb = reinterpret_cast<const unsigned char *>(a.X);
+      for (long long k = 0; k < my_steps; ++k) {
+        const int s = (int)(k % S);
+        const long long use = k / S;
+        if (use > 0) mbar_wait(bars + 8u * (S + s), (uint32_t)((use - 1) & 1));
+        const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * TR;
+        const long long left = a.rows - row0;
+        const uint32_t rv = left < TR ? (uint32_t)left : (uint32_t)TR;
+        const uint32_t full = bars + 8u * s;
+        mbar_expect_tx(full, rv * row_bytes);
+        tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride), Xb + (size_t)row0 * row_bytes, rv * row_bytes, full);
+      }
+    }
+   } else if (warp == NCW) {
+    // ===================== scalar warp: margins -> loss', loss =====================
+    double lossacc = 0.0;
+    double ynext = 0.0;
+    if (lane < TR) {
+      const long long r = (long long)blockIdx.x * TR + lane;
+      if (r < a.rows) ynext = a.labels[r];
+    }
+    for (long long k = 0; k < my_steps; ++k) {
+      const int b = (int)(k & 1);
+      const long long tile = blockIdx.x + k * (long long)gridDim.x;
+      const long long left = a.rows - tile * TR;
+      const int rv = left < TR ? (int)left : TR;
+      const double ylab = ynext;
+      if (lane < TR) {
+        const long long r = (tile + gridDim.x) * TR + lane;
+        if (r < a.rows) ynext = a.labels[r];
+      }
+      named_sync(1 + b, kWsConsumers + 32);  // partials of step k are in shared memory
+      if (lane < TR) {
+        const double *pp = partial + (size_t)(b * kMaxTileRows + lane) * 8;
+        double m = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < WPG; ++wi) m += pp[wi];
+        double mult, loss;
+        loss_eval(a.kind, m, ylab, mult, loss);
+        const bool valid = lane < rv;
+        mult_s[b * kMaxTileRows + lane] = valid ? mult : 0.0;
+        lossacc += valid ? loss : 0.0;
+      }
+      named_arrive(3 + b, kWsConsumers + 32);
+    }
+    for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+    if (lane == 0) slab[a.d] = lossacc;
+   }
+    return;
+  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsConsumerRegs));
+
+  // ===================== consumers =====================
+  const int g = tid / TPR, t = tid % TPR, wig = t >> 5;
+  double wreg[V][EPV], acc[V][EPV];
+  mbar_wait(wbar, 0);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int vec = v * TPR + t;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+      wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
+      acc[v][e] = 0.0;
+    }
+  }
+  double xd[2][R][V][EPV];
+
+  auto phase2 = [&](int b) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const double mu = mult_s[b * kMaxTileRows + g * R + r];
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) acc[v][e] = fma(mu, xd[b][r][v][e], acc[v][e]);
+    }
+  };
+
+  // one pipeline step on buffer B (compile-time, so xd[B] stays in registers)
+  auto step = [&](auto Bc, long long k) {
+    constexpr int B = decltype(Bc)::value;
+    const int s = (int)(k % S);
+    const uint32_t par = (uint32_t)((k / S) & 1);
+    const long long tile = blockIdx.x + k * (long long)gridDim.x;
+    const long long left = a.rows - tile * TR;
+    const int rv = left < TR ? (int)left : TR;
+    mbar_wait(bars + 8u * s, par);
+    const unsigned char *stage = smem + (size_t)s * L.stage_stride;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int vec = v * TPR + t;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)vec * 16);
+        cvt_vec<T, EPV>(raw, xd[B][r][v]);
+      }
+    }
+    if (rv < TR) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (g * R + r >= rv) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) xd[B][r][v][e] = 0.0;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bars + 8u * (S + s));  // stage may be refilled
+    double p[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) sacc = fma(xd[B][r][v][e], wreg[v][e], sacc);
+      p[r] = sacc;
+    }
+    const double tot = warp_rows_reduce<R>(p, lane);
+    if ((lane % (32 / R)) == 0) partial[(size_t)(B * kMaxTileRows + g * R + lane / (32 / R)) * 8 + wig] = tot;
+    named_arrive(1 + B, kWsConsumers + 32);
+    if (k > 0) {  // phase 2 of the previous step, whose loss' values have had a whole step to arrive
+      named_sync(3 + (B ^ 1), kWsConsumers + 32);
+      phase2(B ^ 1);
+    }
+  };
+
+  long long k = 0;
+  for (; k + 1 < my_steps; k += 2) {
+    step(std::integral_constant<int, 0>{}, k);
+    step(std::integral_constant<int, 1>{}, k + 1);
+  }
+  if (k < my_steps) {
+    step(std::integral_constant<int, 0>{}, k);
+    named_sync(3 + 0, kWsConsumers + 32);
+    phase2(0);
+  } else if (my_steps > 0) {
+    named_sync(3 + 1, kWsConsumers + 32);
+    phase2(1);
+  }
+
+  // ---------------- per-CTA slab
+  if (NG > 1) {
+    named_sync(5, kWsConsumers);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) aux[(size_t)g * (TPR * V * EPV) + (v * TPR + t) * EPV + e] = acc[v][e];
+    named_sync(5, kWsConsumers);
+    if (g == 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          double sacc = 0.0;
+          for (int gg = 0; gg < NG; ++gg) sacc += aux[(size_t)gg * (TPR * V * EPV) + (v * TPR + t) * EPV + e];
+          acc[v][e] = sacc;
+        }
+    }
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int vec = v * TPR + t;
+      if (vec < nvec) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) slab[vec * EPV + e] = acc[v][e];
+      }
+    }
   }
 }
 
@@ -389,14 +662,14 @@ inline bool ring_shape(int32_t d, int elem_bytes, RingShape &sh, int &nvec) {
   return false;
 }
 
-template <typename T, int TPR, int V, int R, int MINB>
+template <typename T, int NT, int TPR, int V, int R, int MINB>
 cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
   constexpr int EPV = Elem<T>::EPV;
-  constexpr int NG = kConsumers / TPR;
+  constexpr int NG = NT / TPR;
   constexpr int TR = NG * R;
   K1Args a = a_in;
   const uint32_t row_bytes = (uint32_t)a.d * sizeof(T);
-  const uint32_t tile_bytes = TR * row_bytes;
+  const uint32_t tile_bytes = TR * row_bytes + kMaxTileRows * 8;  // rows + their labels
   uint32_t aux_bytes = (uint32_t)a.d * 8u;
   if (NG > 1) {
     const uint32_t need = (uint32_t)NG * TPR * V * EPV * 8u;
@@ -407,7 +680,7 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
   while (stages > 1 && ring_layout(tile_bytes, aux_bytes, stages).total > budget) --stages;
   a.stages = stages;
   const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages);
-  auto kern = k1_ring_kernel<T, TPR, V, R, MINB>;
+  auto kern = k1_ring_kernel<T, NT, TPR, V, R, MINB>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) return e;
   const long long ntiles = (a.rows + TR - 1) / TR;
@@ -415,7 +688,7 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   *blocks_out = (int)grid;
-  kern<<<(unsigned)grid, kConsumers, L.total, st>>>(a, nvec, ntiles, aux_bytes);
+  kern<<<(unsigned)grid, NT, L.total, st>>>(a, nvec, ntiles, aux_bytes);
   return cudaGetLastError();
 }
 
@@ -424,28 +697,73 @@ cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm
                           cudaStream_t st) {
   if (sh.v == 1) {
     switch (sh.tpr) {
-      case 32: return launch_ring_inst<T, 32, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
-      case 64: return launch_ring_inst<T, 64, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
-      case 128: return launch_ring_inst<T, 128, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
+      case 32: return launch_ring_inst<T, 256, 32, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+      case 64: return launch_ring_inst<T, 256, 64, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
+      case 128: return launch_ring_inst<T, 256, 128, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
       default: {
-        // tuning variants of the headline shape (rows per tile x resident CTAs per SM)
+        // tuning variants of the headline shape: (threads per CTA) x (rows per tile) x (resident CTAs per SM)
         const int key = a.tune_rows * 10 + a.tune_ctas;
         switch (key) {
-          case 81: return launch_ring_inst<T, 256, 1, 8, 1>(a, nvec, sm_count, blocks_out, st);
-          case 42: return launch_ring_inst<T, 256, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
-          case 43: return launch_ring_inst<T, 256, 1, 4, 3>(a, nvec, sm_count, blocks_out, st);
-          default: return launch_ring_inst<T, 256, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
+          case 81: return launch_ring_inst<T, 256, 256, 1, 8, 1>(a, nvec, sm_count, blocks_out, st);
+          case 42: return launch_ring_inst<T, 256, 256, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+          case 43: return launch_ring_inst<T, 256, 256, 1, 4, 3>(a, nvec, sm_count, blocks_out, st);
+          case 44: return launch_ring_inst<T, 128, 128, 2, 4, 4>(a, nvec, sm_count, blocks_out, st);  // 128-thread CTAs
+          case 45: return launch_ring_inst<T, 128, 128, 2, 4, 3>(a, nvec, sm_count, blocks_out, st);
+          default: return launch_ring_inst<T, 256, 256, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
         }
       }
     }
   }
-  if (sh.v == 2) return launch_ring_inst<T, 256, 2, 4, 2>(a, nvec, sm_count, blocks_out, st);
-  return launch_ring_inst<T, 256, 4, 2, 2>(a, nvec, sm_count, blocks_out, st);
+  if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 4, 2>(a, nvec, sm_count, blocks_out, st);
+  return launch_ring_inst<T, 256, 256, 4, 2, 2>(a, nvec, sm_count, blocks_out, st);
+}
+
+
+template <typename T, int TPR, int V, int R>
+cudaError_t launch_ws_inst(const K1Args &a_in, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
+  constexpr int EPV = Elem<T>::EPV;
+  constexpr int NG = kWsConsumers / TPR;
+  constexpr int TR = NG * R;
+  K1Args a = a_in;
+  const uint32_t row_bytes = (uint32_t)a.d * sizeof(T);
+  const uint32_t tile_bytes = TR * row_bytes;
+  uint32_t aux_bytes = (uint32_t)a.d * 8u;
+  const uint32_t need = (uint32_t)NG * TPR * V * EPV * 8u;
+  if (need > aux_bytes) aux_bytes = need;
+  const uint32_t budget = 227u * 1024u - 1024u;
+  int stages = a.stages > 0 ? a.stages : 6;
+  while (stages > 1 && ws_layout(tile_bytes, aux_bytes, stages).total > budget) --stages;
+  a.stages = stages;
+  const WsLayout L = ws_layout(tile_bytes, aux_bytes, stages);
+  auto kern = k1_ws_kernel<T, TPR, V, R>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (a.rows + TR - 1) / TR;
+  long long grid = sm_count;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  *blocks_out = (int)grid;
+  kern<<<(unsigned)grid, kWsThreads, L.total, st>>>(a, nvec, ntiles, aux_bytes);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_ws_t(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
+  if (sh.v == 1) {
+    switch (sh.tpr) {
+      case 32: return launch_ws_inst<T, 32, 1, 2>(a, nvec, sm_count, blocks_out, st);
+      case 64: return launch_ws_inst<T, 64, 1, 4>(a, nvec, sm_count, blocks_out, st);
+      case 128: return launch_ws_inst<T, 128, 1, 4>(a, nvec, sm_count, blocks_out, st);
+      default: return launch_ws_inst<T, 256, 1, 4>(a, nvec, sm_count, blocks_out, st);
+    }
+  }
+  if (sh.v == 2) return launch_ws_inst<T, 256, 2, 2>(a, nvec, sm_count, blocks_out, st);
+  return launch_ws_inst<T, 256, 4, 1>(a, nvec, sm_count, blocks_out, st);
 }
 
 }  // namespace
 
-int k1_max_blocks(int sm_count) { return 3 * sm_count; }
+int k1_max_blocks(int sm_count) { return 4 * sm_count; }
 
 int k1_ring_supported(int32_t d, int elem_bytes) {
   RingShape sh;
@@ -460,6 +778,15 @@ cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *b
   if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
   if (elem_bytes == 4) return launch_ring_t<float>(a, sh, nvec, sm_count, blocks_out, st);
   return launch_ring_t<double>(a, sh, nvec, sm_count, blocks_out, st);
+}
+
+cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
+  RingShape sh;
+  int nvec = 0;
+  if (!ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
+  if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
+  if (elem_bytes == 4) return launch_ws_t<float>(a, sh, nvec, sm_count, blocks_out, st);
+  return launch_ws_t<double>(a, sh, nvec, sm_count, blocks_out, st);
 }
 
 cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,

@@ -59,7 +59,7 @@ def test_smooth_matches_oracle(agd, ctx, oracle, grad, store, shape):
     ds.close()
 
 
-@pytest.mark.parametrize("variant", ["ring", "generic"])
+@pytest.mark.parametrize("variant", ["ring", "generic", "ws"])
 def test_kernel_variants_agree(agd, ctx, oracle, variant):
     rng = np.random.default_rng(5)
     X, y = make_data(rng, 4099, 1024, "logistic", np.float32)
@@ -73,7 +73,30 @@ def test_kernel_variants_agree(agd, ctx, oracle, variant):
     ds.close()
 
 
-@pytest.mark.parametrize("rows,ctas,stages", [(8, 2, 0), (8, 1, 0), (4, 2, 0), (4, 3, 0), (8, 2, 1), (8, 2, 2)])
+@pytest.mark.parametrize("grad", ["logistic", "hinge"])
+@pytest.mark.parametrize("store", ["f32", "f64"])
+@pytest.mark.parametrize("shape", [(3001, 1024), (2000, 512), (515, 256), (260, 128), (777, 2048), (300, 4096), (129, 1100),
+                                   (1, 1024), (7, 1024), (20011, 1024), (40000, 64)])
+def test_ws_kernel_matches_oracle(agd, ctx, oracle, grad, store, shape):
+    """The warp-specialised K1 (dedicated scalar + TMA producer warps, lagged phase 2) on every shape family."""
+    n, d = shape
+    rng = np.random.default_rng(2000 + n + d)
+    X, y = make_data(rng, n, d, grad, np.float32 if store == "f32" else np.float64)
+    w = rng.standard_normal(d) * 0.3 / np.sqrt(d) * 4
+    ds = ctx.parallelize(y, X, store=store)
+    if not (store == "f64" and d > 2048):
+        ds.set_option("k1_variant", "ws")
+    loss, g, cnt = ds.smooth(G(agd, grad), w)
+    ref_loss, ref_g, _ = oracle.smooth(oracle.Data(y, X=X), grad, w, partitions=4, threads=4)
+    assert cnt == n
+    np.testing.assert_allclose(loss, ref_loss, rtol=1e-12)
+    assert rel_err(g, ref_g) < 1e-12
+    a = ds.smooth(G(agd, grad), w)
+    assert a[0] == loss and np.array_equal(a[1], g)      # deterministic
+    ds.close()
+
+
+@pytest.mark.parametrize("rows,ctas,stages", [(8, 2, 0), (8, 1, 0), (4, 2, 0), (4, 3, 0), (8, 2, 1), (8, 2, 2), (4, 4, 0), (4, 5, 0)])
 def test_ring_tuning_variants(agd, ctx, oracle, rows, ctas, stages):
     rng = np.random.default_rng(6)
     X, y = make_data(rng, 70001, 1024, "logistic", np.float32)
