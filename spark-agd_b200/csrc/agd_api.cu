@@ -87,8 +87,8 @@ struct Dev {
   size_t slabs_doubles = 0;
   double *partials = nullptr;
   unsigned int *ticket = nullptr;
-  double *scalars_dev = nullptr;
-  double *scalars_host = nullptr;  // pinned, 2*K3_NS
+  double *scalars_dev = nullptr;   // device alias of scalars_host: K3 writes its scalars straight to the host
+  double *scalars_host = nullptr;  // pinned + mapped, 2*K3_NS
   void *stage_dev = nullptr;
   size_t stage_bytes = 0;
   ncclComm_t comm = nullptr;
@@ -320,8 +320,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
 int read_scalars(agd_handle *h, double *out) {
   Dev &D = h->devs[0];
   CK(cudaSetDevice(D.ordinal));
-  CK(cudaMemcpyAsync(D.scalars_host, D.scalars_dev, K3_NS * sizeof(double), cudaMemcpyDeviceToHost, D.st));
-  CK(cudaStreamSynchronize(D.st));
+  CK(cudaStreamSynchronize(D.st));  // the kernel's zero-copy stores are visible once the stream has drained
   memcpy(out, D.scalars_host, K3_NS * sizeof(double));
   return 0;
 }
@@ -439,9 +438,8 @@ int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
     if (cudaSetDevice(D.ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&D.ticket, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(D.ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
-        cudaMalloc(&D.scalars_dev, 2 * K3_NS * sizeof(double)) != cudaSuccess ||
-        cudaMemset(D.scalars_dev, 0, 2 * K3_NS * sizeof(double)) != cudaSuccess ||
-        cudaMallocHost(&D.scalars_host, 2 * K3_NS * sizeof(double)) != cudaSuccess) {
+        cudaHostAlloc(&D.scalars_host, 2 * K3_NS * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&D.scalars_dev, D.scalars_host, 0) != cudaSuccess) {
       fail(h, "device %d setup failed: %s", D.ordinal, cudaGetErrorString(cudaGetLastError()));
       agd_destroy(nh);
       return 1;
@@ -469,7 +467,7 @@ int agd_destroy(agd_handle *h) {
     cudaStreamSynchronize(D.st);
     if (D.comm && nccl_api().ok) nccl_api().CommDestroy(D.comm);
     free_shard(h, D);
-    double *v[] = {D.x, D.z, D.x_old, D.z_old, D.y, D.g_y, D.g_x, D.wtmp, D.acc, D.slabs, D.partials, D.scalars_dev};
+    double *v[] = {D.x, D.z, D.x_old, D.z_old, D.y, D.g_y, D.g_x, D.wtmp, D.acc, D.slabs, D.partials};
     for (double *p : v)
       if (p) cudaFree(p);
     if (D.ticket) cudaFree(D.ticket);
@@ -796,16 +794,18 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   };
 
   for (int nIter = 1; nIter <= p->num_iterations; ++nIter) {              // :237
-    if (launch_all([&](Dev &D) { return k3_copy2_launch(D.x_old, D.x, D.z_old, D.z, d, D.st); })) return 1;  // :241
     const double L_old = L;                                                // :242
     L = L * p->alpha;                                                      // :243
     const double theta_old = theta;                                        // :244
-    bool nonterminating = false, have_fx = false;
+    bool nonterminating = false, have_fx = false, first_round = true;
     double f_x = 0.0;
     for (;;) {                                                             // :246
       theta = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L / L_old) / (theta_old * theta_old)));  // :248
       const double omt = 1.0 - theta;
-      if (launch_all([&](Dev &D) { return k3_combine_launch(D.y, D.x_old, omt, D.z_old, theta, d, D.st); })) return 1;  // :249
+      if (first_round) {  // (x_old, z_old) = (x, z) :241 fused with y = x_old*(1-theta) + z_old*theta :249
+        if (launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt, theta, d, D.st); })) return 1;
+        first_round = false;
+      } else if (launch_all([&](Dev &D) { return k3_combine_launch(D.y, D.x_old, omt, D.z_old, theta, d, D.st); })) return 1;  // :249
       if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
       s.passes++;
       const double step = 1.0 / (theta * L);                               // :253
@@ -834,7 +834,6 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       {
         Dev &D = h->devs[0];
         CK(cudaSetDevice(D.ordinal));
-        CK(cudaMemcpyAsync(D.scalars_host + K3_NS, D.scalars_dev + K3_NS, K3_NS * sizeof(double), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
         memcpy(sg, D.scalars_host + K3_NS, K3_NS * sizeof(double));
       }
@@ -861,9 +860,10 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       {
         Dev &D = h->devs[0];
         CK(cudaSetDevice(D.ordinal));
-        CK(cudaMemcpyAsync(D.scalars_host + K3_NS, D.acc + d, 2 * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+        double tail[2];
+        CK(cudaMemcpyAsync(tail, D.acc + d, 2 * sizeof(double), cudaMemcpyDeviceToHost, D.st));
         CK(cudaStreamSynchronize(D.st));
-        f_x = D.scalars_host[K3_NS] / D.scalars_host[K3_NS + 1];
+        f_x = tail[0] / tail[1];
       }
     }
     const double c_x = reg_value(p->updater, p->reg_param, sc[2], sc[5]);  // :305  applyProjector(x, g_x, 0.0)._1

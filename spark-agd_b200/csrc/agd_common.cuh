@@ -75,6 +75,9 @@ cudaError_t k3_gx_launch(const K3GxArgs &a, cudaStream_t st);
 // out = a*ca + b*cb (separate roundings, as breeze does at AGD.scala:249)
 cudaError_t k3_combine_launch(double *out, const double *a, double ca, const double *b, double cb, int32_t d,
                               cudaStream_t st);
+// x_old = x ; z_old = z ; y = x*ca + z*cb  (AGD.scala:241 + :249 in one launch)
+cudaError_t k3_begin_launch(double *x_old, double *z_old, double *y, const double *x, const double *z, double ca,
+                            double cb, int32_t d, cudaStream_t st);
 // dst0 = src0 ; dst1 = src1 (either pair may be null)
 cudaError_t k3_copy2_launch(double *dst0, const double *src0, double *dst1, const double *src1, int32_t d,
                             cudaStream_t st);

@@ -623,24 +623,34 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
 }
 
 // ---------------------------------------------------------------- slab reduction (combOp, AGD.scala:201-204)
-__global__ void __launch_bounds__(128) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int d,
+// out[c] = sum over slabs of column c, c <= d.  32 columns per block; 8 slab groups per block sum
+// strided subsets (slab b -> group b % 8) with 4 loads in flight, then group 0 adds the 8 group sums in
+// order: the summation tree is fixed, so the result is bit-reproducible.
+__global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int d,
                                                         long long rows, double *__restrict__ out) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
+  __shared__ double part[8][33];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const size_t stride = (size_t)d + 1;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (c <= d) {
-    const size_t stride = (size_t)d + 1;
-    double s0 = 0.0;
-    int b = 0;
-    for (; b + 8 <= blocks; b += 8) {
-      double v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = slabs[(size_t)(b + i) * stride + c];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s0 += v[i];
+    int b = grp;
+    for (; b + 24 < blocks; b += 32) {
+      const double v0 = slabs[(size_t)b * stride + c], v1 = slabs[(size_t)(b + 8) * stride + c],
+                   v2 = slabs[(size_t)(b + 16) * stride + c], v3 = slabs[(size_t)(b + 24) * stride + c];
+      s0 += v0; s1 += v1; s2 += v2; s3 += v3;
     }
-    for (; b < blocks; ++b) s0 += slabs[(size_t)b * stride + c];
-    out[c] = s0;
+    for (; b < blocks; b += 8) s0 += slabs[(size_t)b * stride + c];
   }
-  if (c == 0) out[d + 1] = (double)rows;
+  part[grp][cl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0 && c <= d) {
+    double t = 0.0;
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi) t += part[gi][cl];
+    out[c] = t;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[d + 1] = (double)rows;
 }
 
 struct RingShape { int tpr, v, r; };
@@ -804,8 +814,8 @@ cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int
 }
 
 cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st) {
-  const int grid = (d + 1 + 127) / 128;
-  k1_reduce_kernel<<<grid, 128, 0, st>>>(slabs, blocks, d, (long long)rows, out);
+  const int grid = (d + 1 + 31) / 32;
+  k1_reduce_kernel<<<grid, 256, 0, st>>>(slabs, blocks, d, (long long)rows, out);
   return cudaGetLastError();
 }
 

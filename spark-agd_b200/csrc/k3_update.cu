@@ -151,6 +151,17 @@ __global__ void __launch_bounds__(kK3Threads) k3_combine_kernel(double *out, con
     out[j] = __dadd_rn(__dmul_rn(a[j], ca), __dmul_rn(b[j], cb));                          // :249
 }
 
+// first inner round of an outer iteration: (x_old, z_old) = (x, z) (AGD.scala:241) fused with y (:249)
+__global__ void __launch_bounds__(kK3Threads) k3_begin_kernel(double *x_old, double *z_old, double *y, const double *x,
+                                                             const double *z, double ca, double cb, int d) {
+  for (int j = blockIdx.x * kK3Threads + threadIdx.x; j < d; j += gridDim.x * kK3Threads) {
+    const double xv = x[j], zv = z[j];
+    x_old[j] = xv;
+    z_old[j] = zv;
+    y[j] = __dadd_rn(__dmul_rn(xv, ca), __dmul_rn(zv, cb));
+  }
+}
+
 __global__ void __launch_bounds__(kK3Threads) k3_copy2_kernel(double *d0, const double *s0, double *d1,
                                                              const double *s1, int d) {
   for (int j = blockIdx.x * kK3Threads + threadIdx.x; j < d; j += gridDim.x * kK3Threads) {
@@ -183,6 +194,11 @@ cudaError_t k3_prox_launch(const K3ProxArgs &a, cudaStream_t st) {
 cudaError_t k3_combine_launch(double *out, const double *a, double ca, const double *b, double cb, int32_t d,
                               cudaStream_t st) {
   k3_combine_kernel<<<k3_blocks(d), kK3Threads, 0, st>>>(out, a, ca, b, cb, d);
+  return cudaGetLastError();
+}
+cudaError_t k3_begin_launch(double *x_old, double *z_old, double *y, const double *x, const double *z, double ca,
+                            double cb, int32_t d, cudaStream_t st) {
+  k3_begin_kernel<<<k3_blocks(d), kK3Threads, 0, st>>>(x_old, z_old, y, x, z, ca, cb, d);
   return cudaGetLastError();
 }
 cudaError_t k3_copy2_launch(double *dst0, const double *src0, double *dst1, const double *src1, int32_t d,
