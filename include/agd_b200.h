@@ -103,7 +103,7 @@ int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t
 
 /* ---- shard loading (replaces RDD[(Double, Vector)] partitions cached on executors, AGD.scala:178) ----
  * agd_reserve fixes the shard geometry of local device `dev` and allocates HBM for `rows_capacity`
- * rows stored as `store_dtype` (AGD_F32 or AGD_F64).  agd_load_dense APPENDS `rows` rows (row-major,
+ * rows stored as `store_dtype` (AGD_F64, AGD_F32 or AGD_BF16; values are rounded to nearest-even).  agd_load_dense APPENDS `rows` rows (row-major,
  * leading dimension ld elements, element type src_dtype AGD_F64|AGD_F32) and their labels.  If the
  * device was not reserved, the first load reserves exactly `rows`. */
 int agd_reserve(agd_handle *h, int32_t dev, int64_t rows_capacity, int32_t d, int32_t store_dtype);

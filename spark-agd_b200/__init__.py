@@ -9,8 +9,8 @@ from . import _native
 from ._native import NativeError, build, exported_symbols
 from .optimization import (AcceleratedGradientDescent, Context, DeviceDataset, Gradient, GradientDescent,
                            HingeGradient, L1Updater, LeastSquaresGradient, LogisticGradient, RunStats,
-                           SimpleUpdater, SquaredL2Updater, Updater, run_with_stats)
+                           SimpleUpdater, SquaredL2Updater, Updater, bf16_to_f32, run_with_stats)
 
 __all__ = ["AcceleratedGradientDescent", "Context", "DeviceDataset", "Gradient", "GradientDescent",
            "HingeGradient", "L1Updater", "LeastSquaresGradient", "LogisticGradient", "NativeError", "RunStats",
-           "SimpleUpdater", "SquaredL2Updater", "Updater", "build", "exported_symbols", "run_with_stats"]
+           "SimpleUpdater", "SquaredL2Updater", "Updater", "bf16_to_f32", "build", "exported_symbols", "run_with_stats"]

@@ -158,7 +158,8 @@ double jmin(double a, double b) {
   return a < b ? a : b;
 }
 
-int dtype_bytes(int dt) { return dt == AGD_F64 ? 8 : (dt == AGD_F32 ? 4 : 0); }
+int dtype_bytes(int dt) { return dt == AGD_F64 ? 8 : (dt == AGD_F32 ? 4 : (dt == AGD_BF16 ? 2 : 0)); }
+int bytes_dtype(int eb) { return eb == 8 ? AGD_F64 : (eb == 4 ? AGD_F32 : AGD_BF16); }
 
 int free_shard(agd_handle *h, Dev &D) {
   CK(cudaSetDevice(D.ordinal));
@@ -211,7 +212,7 @@ int set_dim(agd_handle *h, int32_t d) {
 
 int reserve_locked(agd_handle *h, Dev &D, int64_t cap, int32_t d, int store_dtype) {
   const int eb = dtype_bytes(store_dtype);
-  if (!eb) return fail(h, "store_dtype must be AGD_F32 or AGD_F64");
+  if (!eb) return fail(h, "store_dtype must be AGD_F64, AGD_F32 or AGD_BF16");
   if (cap < 0) return fail(h, "negative capacity");
   CK(cudaSetDevice(D.ordinal));
   Shard &s = D.sh;
@@ -533,7 +534,7 @@ int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype,
   if (!h) return 1;
   if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
   const int sb = dtype_bytes(src_dtype);
-  if (!sb) return fail(h, "src_dtype must be AGD_F32 or AGD_F64");
+  if (sb != 4 && sb != 8) return fail(h, "src_dtype must be AGD_F32 or AGD_F64");
   if (rows < 0 || ld < d) return fail(h, "bad geometry rows=%lld d=%d ld=%lld", (long long)rows, d, (long long)ld);
   if (rows > 0 && (!X || !labels)) return fail(h, "NULL data pointer");
   if (set_dim(h, d)) return 1;
@@ -543,7 +544,7 @@ int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype,
   const int64_t need = s.rows + rows;
   if (s.cap == 0 || need > s.cap) {
     const int64_t cap = s.cap == 0 ? need : (need > 2 * s.cap ? need : 2 * s.cap);
-    if (reserve_locked(h, D, cap, d, s.cap ? (s.elem_bytes == 8 ? AGD_F64 : AGD_F32) : store_dtype)) return 1;
+    if (reserve_locked(h, D, cap, d, s.cap ? bytes_dtype(s.elem_bytes) : store_dtype)) return 1;
   }
   const int eb = s.elem_bytes;
   if (dtype_bytes(store_dtype) != eb) return fail(h, "storage dtype mismatch with the resident shard");
@@ -577,7 +578,7 @@ int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_
   if (!h) return 1;
   if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
   const int sb = dtype_bytes(src_dtype), eb = dtype_bytes(store_dtype);
-  if (!sb || !eb) return fail(h, "dtypes must be AGD_F32 or AGD_F64");
+  if ((sb != 4 && sb != 8) || (eb != 4 && eb != 8)) return fail(h, "CSR dtypes must be AGD_F32 or AGD_F64");
   if (rows < 0 || (rows > 0 && (!rowptr || !labels))) return fail(h, "bad CSR arguments");
   if (set_dim(h, d)) return 1;
   Dev &D = h->devs[dev];
@@ -637,7 +638,7 @@ int32_t agd_dim(const agd_handle *h) { return h ? h->d : 0; }
 int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dtype, uint64_t seed, int32_t gradient) {
   if (!h) return 1;
   const int eb = dtype_bytes(store_dtype);
-  if (!eb) return fail(h, "store_dtype must be AGD_F32 or AGD_F64");
+  if (!eb) return fail(h, "store_dtype must be AGD_F64, AGD_F32 or AGD_BF16");
   if (total_rows < 0) return fail(h, "negative row count");
   if (agd_clear(h)) return 1;
   if (set_dim(h, d)) return 1;

@@ -18,6 +18,7 @@
 //     thread's private column sums (no atomics);
 //   * per-CTA column sums go to a slab; k1_reduce_kernel adds the slabs in fixed order.
 // k1_generic_kernel: any (rows, d), scalar loads, slab accumulators in global memory (L2-resident).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,6 +37,7 @@ constexpr int kMaxTileRows = 32;
 template <typename T> struct Elem;
 template <> struct Elem<float> { static constexpr int EPV = 4; };
 template <> struct Elem<double> { static constexpr int EPV = 2; };
+template <> struct Elem<__nv_bfloat16> { static constexpr int EPV = 8; };
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +82,17 @@ template <>
 __device__ __forceinline__ void cvt_vec<double, 2>(const uint4 &raw, double (&out)[2]) {
   out[0] = __hiloint2double((int)raw.y, (int)raw.x);
   out[1] = __hiloint2double((int)raw.w, (int)raw.z);
+}
+
+template <>
+__device__ __forceinline__ void cvt_vec<__nv_bfloat16, 8>(const uint4 &raw, double (&out)[8]) {
+  // a bf16 is the upper half of an fp32: widen with a shift / mask, then F2F to fp64
+  const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = (double)__uint_as_float(wds[i] << 16);
+    out[2 * i + 1] = (double)__uint_as_float(wds[i] & 0xffff0000u);
+  }
 }
 
 __host__ __device__ inline uint32_t round_up_u32(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -566,6 +579,11 @@ k1_ws_kernel(const K1Args a, const int nvec, const long long ntiles, const uint3
   }
 }
 
+template <typename T> __device__ __forceinline__ double load_elem(const T *p) { return (double)*p; }
+template <> __device__ __forceinline__ double load_elem<__nv_bfloat16>(const __nv_bfloat16 *p) {
+  return (double)__bfloat162float(*p);
+}
+
 // ---------------------------------------------------------------- generic shapes
 template <typename T>
 __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const long long ntiles) {
@@ -589,7 +607,7 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
       const double wc = a.w[c];
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (r < rv) p[r] = fma((double)X[(size_t)(row0 + r) * a.d + c], wc, p[r]);
+        if (r < rv) p[r] = fma(load_elem<T>(&X[(size_t)(row0 + r) * a.d + c]), wc, p[r]);
     }
     const double tot = warp_rows_reduce<R>(p, lane);
     if ((lane & 3) == 0) part[lane >> 2][warp] = tot;
@@ -608,7 +626,7 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
       double sacc = slab[c];
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (r < rv) sacc = fma(mult_s[r], (double)X[(size_t)(row0 + r) * a.d + c], sacc);
+        if (r < rv) sacc = fma(mult_s[r], load_elem<T>(&X[(size_t)(row0 + r) * a.d + c]), sacc);
       slab[c] = sacc;
     }
   }
@@ -658,6 +676,16 @@ inline bool ring_shape(int32_t d, int elem_bytes, RingShape &sh, int &nvec) {
   const int epv = 16 / elem_bytes;
   if (d <= 0 || d % epv != 0) return false;
   nvec = d / epv;
+  if (elem_bytes == 2) {  // bf16: 8 elements per vector, so at most 4 vectors per thread and tile
+    if (nvec <= 256) {
+      int tpr = 32;
+      while (tpr < nvec) tpr <<= 1;
+      sh = {tpr, 1, 4};
+      return true;
+    }
+    if (nvec <= 512) { sh = {256, 2, 2}; return true; }
+    return false;
+  }
   if (nvec <= 256) {
     int tpr = 32;
     while (tpr < nvec) tpr <<= 1;
@@ -700,6 +728,18 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
   *blocks_out = (int)grid;
   kern<<<(unsigned)grid, NT, L.total, st>>>(a, nvec, ntiles, aux_bytes);
   return cudaGetLastError();
+}
+
+cudaError_t launch_ring_bf16(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
+                             cudaStream_t st) {
+  using T = __nv_bfloat16;
+  if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 2, 2>(a, nvec, sm_count, blocks_out, st);
+  switch (sh.tpr) {
+    case 32: return launch_ring_inst<T, 256, 32, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+    case 64: return launch_ring_inst<T, 256, 64, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+    case 128: return launch_ring_inst<T, 256, 128, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+    default: return launch_ring_inst<T, 256, 256, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
+  }
 }
 
 template <typename T>
@@ -786,6 +826,7 @@ cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *b
   int nvec = 0;
   if (!ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
   if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
+  if (elem_bytes == 2) return launch_ring_bf16(a, sh, nvec, sm_count, blocks_out, st);
   if (elem_bytes == 4) return launch_ring_t<float>(a, sh, nvec, sm_count, blocks_out, st);
   return launch_ring_t<double>(a, sh, nvec, sm_count, blocks_out, st);
 }
@@ -793,7 +834,7 @@ cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *b
 cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
   RingShape sh;
   int nvec = 0;
-  if (!ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
+  if (elem_bytes == 2 || !ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
   if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
   if (elem_bytes == 4) return launch_ws_t<float>(a, sh, nvec, sm_count, blocks_out, st);
   return launch_ws_t<double>(a, sh, nvec, sm_count, blocks_out, st);
@@ -808,7 +849,8 @@ cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   *blocks_out = (int)grid;
-  if (elem_bytes == 4) k1_generic_kernel<float><<<(unsigned)grid, 256, 0, st>>>(a, ntiles);
+  if (elem_bytes == 2) k1_generic_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(a, ntiles);
+  else if (elem_bytes == 4) k1_generic_kernel<float><<<(unsigned)grid, 256, 0, st>>>(a, ntiles);
   else k1_generic_kernel<double><<<(unsigned)grid, 256, 0, st>>>(a, ntiles);
   return cudaGetLastError();
 }

@@ -11,6 +11,7 @@
 //   e_i       : counter (i_lo, i_hi, 0, 4), t from (r0,r1) ;  e = (double)t * (sqrt(3)/65536)
 //   labels    : logistic y = 1[x.w_true + log(u) - log(1-u) > 0] ; least squares y = x.w_true + 0.1 e ;
 //               hinge y = 1[x.w_true > 0] flipped when u < 0.05
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,6 +36,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
 __device__ __forceinline__ int irwin_hall4(uint32_t a, uint32_t b) {
   return (int)((a & 0xffffu) + (a >> 16) + (b & 0xffffu) + (b >> 16)) - 131070;
 }
+template <typename T> __device__ __forceinline__ T from_f32(float v) { return (T)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ double to_f64(T v) { return (double)v; }
+template <> __device__ __forceinline__ double to_f64<__nv_bfloat16>(__nv_bfloat16 v) { return (double)__bfloat162float(v); }
+template <typename D, typename S> __device__ __forceinline__ D convert_elem(S v) { return (D)v; }
+template <> __device__ __forceinline__ __nv_bfloat16 convert_elem<__nv_bfloat16, float>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 convert_elem<__nv_bfloat16, double>(double v) { return __double2bfloat16(v); }
+
 __device__ __forceinline__ float synth_x_scale() { return (float)(1.7320508075688772 / 65536.0); }
 
 template <typename T>
@@ -52,8 +61,8 @@ __global__ void __launch_bounds__(256) synth_dense_kernel(T *X, uint64_t seed, l
     const float x0 = __fmul_rn((float)irwin_hall4(o[0], o[1]), scale);
     const float x1 = __fmul_rn((float)irwin_hall4(o[2], o[3]), scale);
     T *row = X + (size_t)r * d;
-    row[2 * jp] = (T)x0;
-    if (2 * jp + 1 < d) row[2 * jp + 1] = (T)x1;
+    row[2 * jp] = from_f32<T>(x0);  // bf16 storage: the fp32 spec value rounded to nearest-even
+    if (2 * jp + 1 < d) row[2 * jp + 1] = from_f32<T>(x1);
   }
 }
 
@@ -76,7 +85,7 @@ __global__ void __launch_bounds__(256) synth_labels_kernel(const T *X, const dou
   for (long long r = warp_global; r < rows; r += nwarps) {
     const T *row = X + (size_t)r * d;
     double m = 0.0;
-    for (int j = lane; j < d; j += 32) m = fma((double)row[j], w_true[j], m);
+    for (int j = lane; j < d; j += 32) m = fma(to_f64<T>(row[j]), w_true[j], m);
     for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(0xffffffffu, m, off);
     if (lane == 0) {
       const unsigned long long i = (unsigned long long)(row0 + r);
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(D *dst, const S *src,
   for (long long q = blockIdx.x * 256LL + threadIdx.x; q < total; q += (long long)gridDim.x * 256LL) {
     const long long r = q / d;
     const int j = (int)(q - r * d);
-    dst[q] = (D)src[r * ld + j];
+    dst[q] = convert_elem<D, S>(src[r * ld + j]);
   }
 }
 
@@ -122,7 +131,9 @@ cudaError_t synth_dense_launch(void *X, int elem_bytes, uint64_t seed, int64_t r
                                cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   const long long total = rows * (long long)((d + 1) / 2);
-  if (elem_bytes == 4)
+  if (elem_bytes == 2)
+    synth_dense_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>((__nv_bfloat16 *)X, seed, row0, rows, d);
+  else if (elem_bytes == 4)
     synth_dense_kernel<float><<<grid_for(total), 256, 0, st>>>((float *)X, seed, row0, rows, d);
   else
     synth_dense_kernel<double><<<grid_for(total), 256, 0, st>>>((double *)X, seed, row0, rows, d);
@@ -138,7 +149,9 @@ cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_t
                                 int kind, int64_t row0, int64_t rows, int32_t d, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = grid_for(rows * 32);
-  if (elem_bytes == 4)
+  if (elem_bytes == 2)
+    synth_labels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)X, w_true, labels, seed, kind, row0, rows, d);
+  else if (elem_bytes == 4)
     synth_labels_kernel<float><<<grid, 256, 0, st>>>((const float *)X, w_true, labels, seed, kind, row0, rows, d);
   else
     synth_labels_kernel<double><<<grid, 256, 0, st>>>((const double *)X, w_true, labels, seed, kind, row0, rows, d);
@@ -149,7 +162,11 @@ cudaError_t convert_rows_launch(void *dst, int dst_bytes, const void *src, int s
                                 int64_t ld, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = grid_for(rows * (long long)d);
-  if (dst_bytes == 4 && src_bytes == 4)
+  if (dst_bytes == 2 && src_bytes == 4)
+    convert_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((__nv_bfloat16 *)dst, (const float *)src, rows, d, ld);
+  else if (dst_bytes == 2 && src_bytes == 8)
+    convert_rows_kernel<__nv_bfloat16, double><<<grid, 256, 0, st>>>((__nv_bfloat16 *)dst, (const double *)src, rows, d, ld);
+  else if (dst_bytes == 4 && src_bytes == 4)
     convert_rows_kernel<float, float><<<grid, 256, 0, st>>>((float *)dst, (const float *)src, rows, d, ld);
   else if (dst_bytes == 4 && src_bytes == 8)
     convert_rows_kernel<float, double><<<grid, 256, 0, st>>>((float *)dst, (const double *)src, rows, d, ld);

@@ -80,7 +80,12 @@ def _upd_kind(u) -> int:
 
 
 _DT = {np.dtype(np.float64): N.F64, np.dtype(np.float32): N.F32}
-_STORE = {"f32": N.F32, "f64": N.F64, N.F32: N.F32, N.F64: N.F64}
+_STORE = {"f32": N.F32, "f64": N.F64, "bf16": N.BF16, N.F32: N.F32, N.F64: N.F64, N.BF16: N.BF16}
+
+
+def bf16_to_f32(raw: np.ndarray) -> np.ndarray:
+    """Exact widening of raw bf16 bit patterns (uint16) to float32."""
+    return (raw.astype(np.uint32) << 16).view(np.float32)
 
 
 def _ptr(a):
@@ -216,6 +221,7 @@ class DeviceDataset:
         return int(N.lib().agd_rows(self.h, dev))
 
     def get_rows(self, dev: int, row0: int, rows: int, dtype=np.float32):
+        """Rows as stored (dtype must match the storage: float32, float64, or uint16 for raw bf16)."""
         X = np.empty((rows, self.d), dtype=dtype)
         y = np.empty(rows, dtype=np.float64)
         N.check(N.lib().agd_get_rows(self.h, dev, row0, rows, _ptr(X), _ptr(y)), self.h)

@@ -176,6 +176,49 @@ def test_logistic_extreme_margins(agd, ctx, oracle, scale, d):
     ds.close()
 
 
+# ------------------------------------------------------------------ bf16 storage
+def f32_to_bf16_bits(x):
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + 0x7FFF + ((b >> 16) & 1)) >> 16).astype(np.uint16)       # round to nearest even
+
+
+@pytest.mark.parametrize("grad", ["logistic", "least_squares", "hinge"])
+@pytest.mark.parametrize("shape", [(3001, 1024), (2000, 512), (515, 256), (777, 2048), (300, 4096), (129, 1104),
+                                   (37, 40), (10, 20000), (64, 8192), (5, 3)])
+def test_bf16_storage_matches_oracle(agd, ctx, oracle, grad, shape):
+    """X stored as bf16 in HBM (rounded to nearest-even at load), widened to fp64 in the kernel: compare with
+    the oracle run on exactly the stored values."""
+    n, d = shape
+    rng = np.random.default_rng(3000 + n + d)
+    X, y = make_data(rng, n, d, grad, np.float32)
+    w = rng.standard_normal(d) * 0.3 / np.sqrt(d) * 4
+    ds = ctx.parallelize(y, X, store="bf16")
+    raw, yb = ds.get_rows(0, 0, n, dtype=np.uint16)
+    assert np.array_equal(raw, f32_to_bf16_bits(X)) and np.array_equal(yb, y)
+    Xs = agd.bf16_to_f32(raw)
+    loss, g, cnt = ds.smooth(G(agd, grad), w)
+    ref_loss, ref_g, _ = oracle.smooth(oracle.Data(y, X=Xs), grad, w, partitions=2)
+    assert cnt == n
+    np.testing.assert_allclose(loss, ref_loss, rtol=1e-12)
+    assert rel_err(g, ref_g) < 1e-12
+    ds.close()
+
+
+def test_bf16_run_and_generator(agd, ctx, oracle):
+    n, d = 20000, 1024
+    ds = ctx.synthetic(n, d, agd.LeastSquaresGradient(), seed=7, store="bf16")
+    raw, y = ds.get_rows(0, 0, n, dtype=np.uint16)
+    assert np.array_equal(raw, f32_to_bf16_bits(oracle.synth_dense_f32(7, 0, n, d)))   # spec value, rounded once
+    Xs = agd.bf16_to_f32(raw)
+    w0 = np.zeros(d)
+    w, hist, st = agd.run_with_stats(ds, agd.LeastSquaresGradient(), agd.SquaredL2Updater(), 0.0, 10, 0.01, w0)
+    ref = oracle.agd_run(oracle.Data(y, X=Xs), "least_squares", "squared_l2", w0, convergence_tol=0.0,
+                         num_iterations=10, reg_param=0.01, partitions=4, threads=4)
+    np.testing.assert_allclose(hist, ref.loss_history, rtol=1e-11)
+    assert rel_err(w, ref.weights) < 1e-9 and st.passes == ref.passes
+    ds.close()
+
+
 # ------------------------------------------------------------------ CSR rows (SparseVector)
 @pytest.mark.parametrize("grad", GRADS)
 @pytest.mark.parametrize("store", ["f32", "f64"])
