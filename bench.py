@@ -39,6 +39,11 @@ def parse():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--workload", default="logistic_f32", choices=["logistic_f32", "ls_bf16", "hinge_csr"],
+                    help="logistic_f32 = BASELINE configs[1] (the metric; also configs[4] with --rows 100000000 --dim 512); "
+                         "ls_bf16 = configs[3] shape (--rows 50000000 --dim 4096); hinge_csr = configs[2] shape "
+                         "(--rows 100000000 --dim 1000000 --nnz 64)")
+    ap.add_argument("--nnz", type=int, default=64, help="stored entries per row for hinge_csr")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = auto)")
@@ -188,13 +193,25 @@ def run_b200(args):
 
     d = args.dim
     total_rows = args.rows * (world if args.scaling == "weak" else 1)
-    grad, upd = S.LogisticGradient(), S.SimpleUpdater()
-    data = ctx.synthetic(total_rows, d, grad, seed=SEED, store="f32")     # K0: never timed
+    wl = args.workload
+    reg = 0.0
+    if wl == "logistic_f32":
+        grad, upd, store, eb = S.LogisticGradient(), S.SimpleUpdater(), "f32", 4
+        data = ctx.synthetic(total_rows, d, grad, seed=SEED, store=store)     # K0: never timed
+    elif wl == "ls_bf16":
+        grad, upd, store, eb = S.LeastSquaresGradient(), S.SimpleUpdater(), "bf16", 2
+        data = ctx.synthetic(total_rows, d, grad, seed=SEED, store=store)
+    else:
+        grad, upd, store, eb, reg = S.HingeGradient(), S.SquaredL2Updater(), "f32", 4, 0.1
+        data = ctx.synthetic_csr(total_rows, d, args.nnz, grad, seed=SEED, store=store)
     rows_local = data.local_rows(0)
     w0 = np.zeros(d)
+    if wl != "logistic_f32":
+        args.no_e2e = True
+        args.no_cpu_baseline = True
 
     def run(ds, iters, memoize=False):
-        return S.run_with_stats(ds, grad, upd, 0.0, iters, 0.0, w0, memoize=memoize)
+        return S.run_with_stats(ds, grad, upd, 0.0, iters, reg, w0, memoize=memoize)
 
     # ---- warm-up, then EXACTLY K timed steps, barrier + synchronize on both sides
     barrier()
@@ -217,10 +234,15 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (K1), CUDA events on its own stream inside the timed region
     peak, peak_src = peaks()
     k1_ms = st.k1_ms_total / max(st.k1_launches, 1)
-    alg_bytes = rows_local * (d * 4 + 8)          # fp32 row + fp64 label, per launch
+    if wl == "hinge_csr":
+        alg_bytes = rows_local * (args.nnz * (4 + eb) + 16)   # idx + value per entry, rowptr + label per row
+    else:
+        alg_bytes = rows_local * (d * eb + 8)     # stored row + fp64 label, per launch
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k1_ring_kernel<float,256,1,8,2>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows_local, d),
+    kname = {"logistic_f32": "k1_ring_kernel<float,...>", "ls_bf16": "k1_ring_kernel<__nv_bfloat16,...>",
+             "hinge_csr": "k1_csr_kernel<float>"}[wl]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows_local, d) if wl == "logistic_f32" else None,
                 "peak_source": peak_src, "bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
                 "k1_share_of_step": st.k1_ms_total / st.device_ms_total}
 
@@ -241,12 +263,17 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (wl == "logistic_f32" and total_rows == 10_000_000 and d == 1024) else
+            f"AGD examples/sec (rows x applySmooth passes / s), {wl} {total_rows} x {d}", "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"logistic-loss AGD, {total_rows} x {d} dense fp32 (BASELINE configs[1]), "
-                                   f"SimpleUpdater, w0 = 0, convergenceTol 0, defaults L0=1 beta=.5 alpha=.9 restart",
-                       "rows": total_rows, "d": d, "store": "f32", "rows_per_gpu": rows_local,
+            "config": {"workload": {"logistic_f32": f"logistic-loss AGD, {total_rows} x {d} dense fp32 (BASELINE configs[1]), "
+                                                    f"SimpleUpdater, w0 = 0, convergenceTol 0, defaults L0=1 beta=.5 alpha=.9 restart",
+                                    "ls_bf16": f"least-squares AGD, {total_rows} x {d} dense bf16 storage (BASELINE configs[3] shape), "
+                                               f"CUDA-core fp64 path",
+                                    "hinge_csr": f"hinge-loss + L2 (reg 0.1) AGD, {total_rows} x {d} CSR, {args.nnz} stored entries per "
+                                                 f"row (BASELINE configs[2] shape)"}[wl],
+                       "rows": total_rows, "d": d, "store": store, "rows_per_gpu": rows_local,
                        "parallelism": f"row shards x{world}, one all-reduce of d+2 fp64 per pass",
                        "l2": "inputs larger than L2: every pass streams the whole shard "
                              f"({alg_bytes / 1e9:.2f} GB) from HBM"},

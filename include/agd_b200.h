@@ -109,7 +109,8 @@ int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t
 int agd_reserve(agd_handle *h, int32_t dev, int64_t rows_capacity, int32_t d, int32_t store_dtype);
 int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype, const double *labels,
                    int64_t rows, int32_t d, int64_t ld, int32_t store_dtype);
-/* SparseVector rows as CSR (values src_dtype AGD_F64|AGD_F32, stored as store_dtype). */
+/* SparseVector rows as CSR (values src_dtype AGD_F64|AGD_F32, stored as store_dtype AGD_F64|AGD_F32).
+ * APPENDS `rows` rows: rowptr has rows+1 entries starting at 0 and is rebased onto the resident shard. */
 int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_t *idx, const void *val,
                  int32_t src_dtype, const double *labels, int64_t rows, int32_t d, int32_t store_dtype);
 /* Drops every shard (all local devices). */
@@ -126,6 +127,12 @@ int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dty
                  int32_t gradient);
 int agd_get_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, void *X_out, double *labels_out);
 int agd_synth_wtrue(agd_handle *h, uint64_t seed, int32_t d, double *w_out);
+/* CSR flavour of the synthetic workload: exactly nnz_per_row stored entries per row, strictly increasing
+ * column ids (stratified), same label rules.  agd_get_csr_rows downloads a row range (rowptr rebased to 0). */
+int agd_generate_csr(agd_handle *h, int64_t total_rows, int32_t d, int32_t nnz_per_row, int32_t store_dtype,
+                     uint64_t seed, int32_t gradient);
+int agd_get_csr_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, int64_t *rowptr_out, int32_t *idx_out,
+                     void *val_out, int64_t nnz_capacity, double *labels_out);
 
 /* ---- plug-in granularity entry points (host buffers in and out) ----
  * agd_smooth = applySmooth (AGD.scala:192-208): loss/count and grad/count over ALL shards of the

@@ -81,6 +81,9 @@ void oracle_synth_wtrue(uint64_t seed, int32_t d, double *w);
 void oracle_synth_labels(uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, const float *X,
                          const double *w_true, double *labels);
 
+void oracle_synth_csr_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, int32_t k, int64_t *rowptr,
+                          int32_t *idx, float *val);
+
 #ifdef __cplusplus
 }
 #endif

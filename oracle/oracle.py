@@ -206,5 +206,14 @@ def synth_labels(seed: int, gradient: str, row0: int, X: np.ndarray, w_true: np.
     return y
 
 
+def synth_csr_f32(seed: int, row0: int, rows: int, d: int, k: int):
+    rowptr = np.empty(rows + 1, dtype=np.int64)
+    idx = np.empty(rows * k, dtype=np.int32)
+    val = np.empty(rows * k, dtype=np.float32)
+    lib().oracle_synth_csr_f32(C.c_uint64(seed), C.c_int64(row0), C.c_int64(rows), C.c_int32(d), C.c_int32(k),
+                               _p(rowptr), _p(idx), _p(val))
+    return rowptr, idx, val
+
+
 def max_threads() -> int:
     return lib().oracle_max_threads()

@@ -105,3 +105,26 @@ void oracle_synth_labels(uint64_t seed, int kind, int64_t row0, int64_t rows, in
     }
   }
 }
+
+/* CSR flavour (spec in spark-agd_b200/csrc/synth.cu): exactly k entries per row, entry t of row i from
+ * counter (i_lo, i_hi, t, 5): col = t*(d/k) + r0 % (d/k), value = irwin_hall4(r1, r2) * (float)(sqrt(3)/65536). */
+void oracle_synth_csr_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, int32_t k, int64_t *rowptr,
+                          int32_t *idx, float *val) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t stride = (uint32_t)(d / k);
+  const float scale = (float)kScale64;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+  for (int64_t r = 0; r < rows; ++r) {
+    const uint64_t i = (uint64_t)(row0 + r);
+    rowptr[r] = r * (int64_t)k;
+    for (int32_t t = 0; t < k; ++t) {
+      uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)t, 5u}, o[4];
+      philox4x32_10(k0, k1, c, o);
+      idx[r * (int64_t)k + t] = (int32_t)((uint32_t)t * stride + o[0] % stride);
+      val[r * (int64_t)k + t] = (float)irwin_hall4(o[1], o[2]) * scale;
+    }
+  }
+  rowptr[rows] = rows * (int64_t)k;
+}

@@ -78,6 +78,9 @@ _SIGNATURES = {
     "agd_generate": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32]),
     "agd_get_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "agd_synth_wtrue": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]),
+    "agd_generate_csr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_int32]),
+    "agd_get_csr_rows": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_void_p]),
     "agd_smooth": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
                              C.POINTER(C.c_int64)]),
     "agd_prox": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,

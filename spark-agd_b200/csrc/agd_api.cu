@@ -71,7 +71,7 @@ struct Shard {
   int64_t *rowptr = nullptr;
   int32_t *idx = nullptr;
   void *val = nullptr;
-  int64_t nnz = 0;
+  int64_t nnz = 0, nnz_cap = 0;
 };
 
 struct Dev {
@@ -573,6 +573,47 @@ int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype,
   return 0;
 }
 
+// grows the CSR arrays of a device to hold `rows_cap` rows and `nnz_cap` entries (contents preserved)
+static int csr_reserve_locked(agd_handle *h, Dev &D, int64_t rows_cap, int64_t nnz_cap, int eb) {
+  Shard &s = D.sh;
+  CK(cudaSetDevice(D.ordinal));
+  if (!s.csr && (s.cap > 0 || s.rows > 0)) return fail(h, "device already holds a dense shard");
+  if (s.csr && s.elem_bytes != eb) return fail(h, "storage dtype mismatch with the resident shard");
+  if (rows_cap > s.cap || !s.rowptr) {
+    int64_t *nr = nullptr;
+    double *nl = nullptr;
+    CK(cudaMalloc(&nr, ((size_t)rows_cap + 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&nl, ((size_t)rows_cap + 64) * sizeof(double)));
+    if (s.rowptr) {
+      CK(cudaMemcpyAsync(nr, s.rowptr, ((size_t)s.rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, D.st));
+      CK(cudaMemcpyAsync(nl, s.labels, (size_t)s.rows * sizeof(double), cudaMemcpyDeviceToDevice, D.st));
+    } else {
+      CK(cudaMemsetAsync(nr, 0, sizeof(int64_t), D.st));
+    }
+    CK(cudaStreamSynchronize(D.st));
+    if (s.rowptr) cudaFree(s.rowptr);
+    if (s.labels) cudaFree(s.labels);
+    s.rowptr = nr; s.labels = nl; s.cap = rows_cap;
+  }
+  if (nnz_cap > s.nnz_cap || !s.idx) {
+    int32_t *ni = nullptr;
+    void *nv = nullptr;
+    CK(cudaMalloc(&ni, ((size_t)nnz_cap + 4) * sizeof(int32_t)));
+    CK(cudaMalloc(&nv, ((size_t)nnz_cap + 4) * eb));
+    if (s.idx && s.nnz > 0) {
+      CK(cudaMemcpyAsync(ni, s.idx, (size_t)s.nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, D.st));
+      CK(cudaMemcpyAsync(nv, s.val, (size_t)s.nnz * eb, cudaMemcpyDeviceToDevice, D.st));
+    }
+    CK(cudaStreamSynchronize(D.st));
+    if (s.idx) cudaFree(s.idx);
+    if (s.val) cudaFree(s.val);
+    s.idx = ni; s.val = nv; s.nnz_cap = nnz_cap;
+  }
+  s.csr = true;
+  s.elem_bytes = eb;
+  return 0;
+}
+
 int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_t *idx, const void *val,
                  int32_t src_dtype, const double *labels, int64_t rows, int32_t d, int32_t store_dtype) {
   if (!h) return 1;
@@ -584,36 +625,83 @@ int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_
   Dev &D = h->devs[dev];
   std::lock_guard<std::mutex> g(*D.mu);
   Shard &s = D.sh;
-  if (s.rows > 0 || s.cap > 0) return fail(h, "CSR shards are loaded in one call per device; call agd_clear first");
-  CK(cudaSetDevice(D.ordinal));
   const int64_t nnz = rows > 0 ? rowptr[rows] - rowptr[0] : 0;
   if (rows > 0 && rowptr[0] != 0) return fail(h, "rowptr[0] must be 0");
-  CK(cudaMalloc(&s.rowptr, ((size_t)rows + 1) * sizeof(int64_t)));
-  CK(cudaMalloc(&s.idx, ((size_t)nnz + 4) * sizeof(int32_t)));
-  CK(cudaMalloc(&s.val, ((size_t)nnz + 4) * eb));
-  CK(cudaMalloc(&s.labels, ((size_t)rows + 64) * sizeof(double)));
+  // APPENDS rows (Spark hands partitions over one at a time); arrays grow geometrically
+  const int64_t need_rows = s.rows + rows, need_nnz = s.nnz + nnz;
+  const int64_t rows_cap = need_rows > s.cap ? (need_rows > 2 * s.cap ? need_rows : 2 * s.cap) : s.cap;
+  const int64_t nnz_cap = need_nnz > s.nnz_cap ? (need_nnz > 2 * s.nnz_cap ? need_nnz : 2 * s.nnz_cap) : s.nnz_cap;
+  if (csr_reserve_locked(h, D, rows_cap, nnz_cap, eb)) return 1;
   if (rows > 0) {
-    CK(cudaMemcpyAsync(s.rowptr, rowptr, ((size_t)rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, D.st));
-    CK(cudaMemcpyAsync(s.labels, labels, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, D.st));
-  } else {
-    CK(cudaMemsetAsync(s.rowptr, 0, sizeof(int64_t), D.st));
+    // device rowptr entries for the new rows = host rowptr[1..rows] + resident nnz
+    if (ensure_stage(h, D, ((size_t)rows + 1) * sizeof(int64_t) + (size_t)nnz * sb + 64)) return 1;
+    CK(cudaMemcpyAsync(D.stage_dev, rowptr, ((size_t)rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, D.st));
+    CK(csr_shift_rowptr_launch(s.rowptr + s.rows, (const int64_t *)D.stage_dev, rows + 1, s.nnz, D.st));
+    CK(cudaMemcpyAsync(s.labels + s.rows, labels, (size_t)rows * sizeof(double), cudaMemcpyHostToDevice, D.st));
   }
   if (nnz > 0) {
-    CK(cudaMemcpyAsync(s.idx, idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemcpyAsync(s.idx + s.nnz, idx, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, D.st));
     if (sb == eb) {
-      CK(cudaMemcpyAsync(s.val, val, (size_t)nnz * eb, cudaMemcpyHostToDevice, D.st));
+      CK(cudaMemcpyAsync((unsigned char *)s.val + (size_t)s.nnz * eb, val, (size_t)nnz * eb, cudaMemcpyHostToDevice, D.st));
     } else {
-      if (ensure_stage(h, D, (size_t)nnz * sb)) return 1;
-      CK(cudaMemcpyAsync(D.stage_dev, val, (size_t)nnz * sb, cudaMemcpyHostToDevice, D.st));
-      CK(convert_rows_launch(s.val, eb, D.stage_dev, sb, nnz, 1, 1, D.st));
+      unsigned char *stage_vals = (unsigned char *)D.stage_dev + (((size_t)rows + 1) * sizeof(int64_t) + 63) / 64 * 64;
+      CK(cudaMemcpyAsync(stage_vals, val, (size_t)nnz * sb, cudaMemcpyHostToDevice, D.st));
+      CK(convert_rows_launch((unsigned char *)s.val + (size_t)s.nnz * eb, eb, stage_vals, sb, nnz, 1, 1, D.st));
     }
   }
   CK(cudaStreamSynchronize(D.st));
-  s.csr = true;
-  s.rows = rows;
-  s.cap = rows;
-  s.nnz = nnz;
-  s.elem_bytes = eb;
+  s.rows = need_rows;
+  s.nnz = need_nnz;
+  return 0;
+}
+
+int agd_generate_csr(agd_handle *h, int64_t total_rows, int32_t d, int32_t nnz_per_row, int32_t store_dtype,
+                     uint64_t seed, int32_t gradient) {
+  if (!h) return 1;
+  const int eb = dtype_bytes(store_dtype);
+  if (eb != 4 && eb != 8) return fail(h, "CSR store_dtype must be AGD_F32 or AGD_F64");
+  if (total_rows < 0 || nnz_per_row < 1 || nnz_per_row > d) return fail(h, "bad CSR geometry");
+  if (agd_clear(h)) return 1;
+  if (set_dim(h, d)) return 1;
+  for (size_t i = 0; i < h->devs.size(); ++i) {
+    Dev &D = h->devs[i];
+    std::lock_guard<std::mutex> g(*D.mu);
+    const long long rank = h->first_rank + (long long)i, W = h->world;
+    const int64_t lo = (int64_t)(((__int128)rank * total_rows) / W), hi = (int64_t)(((__int128)(rank + 1) * total_rows) / W);
+    if (csr_reserve_locked(h, D, hi - lo, (hi - lo) * nnz_per_row, eb)) return 1;
+    if (ensure_vectors(h, D, d)) return 1;
+    CK(cudaSetDevice(D.ordinal));
+    CK(synth_wtrue_launch(D.wtmp, seed, d, D.st));
+    CK(synth_csr_launch(D.sh.rowptr, D.sh.idx, D.sh.val, eb, D.wtmp, D.sh.labels, seed, gradient, lo, hi - lo, d,
+                        nnz_per_row, D.st));
+    D.sh.rows = hi - lo;
+    D.sh.nnz = (hi - lo) * nnz_per_row;
+  }
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
+  return 0;
+}
+
+int agd_get_csr_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, int64_t *rowptr_out, int32_t *idx_out,
+                     void *val_out, int64_t nnz_capacity, double *labels_out) {
+  if (!h) return 1;
+  if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
+  Dev &D = h->devs[dev];
+  const Shard &s = D.sh;
+  if (!s.csr) return fail(h, "agd_get_csr_rows serves CSR shards only");
+  if (row0 < 0 || rows < 0 || row0 + rows > s.rows) return fail(h, "row range out of bounds");
+  CK(cudaSetDevice(D.ordinal));
+  CK(cudaMemcpyAsync(rowptr_out, s.rowptr + row0, ((size_t)rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, D.st));
+  CK(cudaStreamSynchronize(D.st));
+  const int64_t a = rowptr_out[0], b = rowptr_out[rows];
+  if (b - a > nnz_capacity) return fail(h, "nnz_capacity too small: need %lld", (long long)(b - a));
+  if (b > a) {
+    CK(cudaMemcpyAsync(idx_out, s.idx + a, (size_t)(b - a) * sizeof(int32_t), cudaMemcpyDeviceToHost, D.st));
+    CK(cudaMemcpyAsync(val_out, (const unsigned char *)s.val + (size_t)a * s.elem_bytes, (size_t)(b - a) * s.elem_bytes,
+                       cudaMemcpyDeviceToHost, D.st));
+  }
+  if (labels_out && rows) CK(cudaMemcpyAsync(labels_out, s.labels + row0, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, D.st));
+  CK(cudaStreamSynchronize(D.st));
+  for (int64_t i = rows; i >= 0; --i) rowptr_out[i] -= a;
   return 0;
 }
 

@@ -103,6 +103,13 @@ cudaError_t synth_wtrue_launch(double *w, uint64_t seed, int32_t d, cudaStream_t
 cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_true, double *labels, uint64_t seed,
                                 int kind, int64_t row0, int64_t rows, int32_t d, cudaStream_t st);
 
+cudaError_t synth_csr_launch(int64_t *rowptr, int32_t *idx, void *val, int elem_bytes, const double *w_true,
+                             double *labels, uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, int32_t k,
+                             cudaStream_t st);
+
+// dst[i] = src[i] + shift (rebasing an appended partition's rowptr onto the resident CSR shard)
+cudaError_t csr_shift_rowptr_launch(int64_t *dst, const int64_t *src, int64_t n, int64_t shift, cudaStream_t st);
+
 // ---------------------------------------------------------------- load path
 // dst (store dtype, ld == d) <- src (src dtype, leading dimension ld), rows x d
 cudaError_t convert_rows_launch(void *dst, int dst_bytes, const void *src, int src_bytes, int64_t rows, int32_t d,

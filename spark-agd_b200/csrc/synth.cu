@@ -108,6 +108,58 @@ __global__ void __launch_bounds__(256) synth_labels_kernel(const T *X, const dou
   }
 }
 
+// CSR synthetic rows: exactly k stored entries per row, strictly increasing column ids by stratification
+//   entry t of row i: counter (i_lo, i_hi, t, 5) -> col = t*(d/k) + r0 % (d/k) ; value = irwin_hall4(r1, r2) * sqrt(3)/65536
+template <typename T>
+__global__ void __launch_bounds__(256) synth_csr_kernel(long long *rowptr, int *idx, T *val, uint64_t seed,
+                                                       long long row0, long long rows, int d, int k) {
+  const long long total = rows * (long long)k;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const uint32_t stride = (uint32_t)(d / k);
+  const float scale = synth_x_scale();
+  for (long long q = blockIdx.x * 256LL + threadIdx.x; q < total; q += (long long)gridDim.x * 256LL) {
+    const long long r = q / k;
+    const int t = (int)(q - r * k);
+    const unsigned long long i = (unsigned long long)(row0 + r);
+    uint32_t o[4];
+    philox4x32_10(k0, k1, (uint32_t)i, (uint32_t)(i >> 32), (uint32_t)t, 5u, o);
+    idx[q] = (int)((uint32_t)t * stride + o[0] % stride);
+    val[q] = from_f32<T>(__fmul_rn((float)irwin_hall4(o[1], o[2]), scale));
+    if (t == 0) rowptr[r] = r * (long long)k;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) rowptr[rows] = total;
+}
+
+// labels for CSR rows (one warp per row)
+template <typename T>
+__global__ void __launch_bounds__(256) synth_csr_labels_kernel(const long long *rowptr, const int *idx, const T *val,
+                                                              const double *w_true, double *labels, uint64_t seed,
+                                                              int kind, long long row0, long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * 256LL + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * 256LL) >> 5;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    double m = 0.0;
+    for (long long q = rowptr[r] + lane; q < rowptr[r + 1]; q += 32) m = fma(to_f64<T>(val[q]), w_true[idx[q]], m);
+    for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(0xffffffffu, m, off);
+    if (lane == 0) {
+      const unsigned long long i = (unsigned long long)(row0 + r);
+      uint32_t o[4];
+      philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)(i >> 32), 0u, 3u, o);
+      const double u = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6) + 0.5) * 0x1.0p-53;
+      double y;
+      if (kind == AGD_GRAD_LOGISTIC) y = (m + log(u) - log(1.0 - u) > 0) ? 1.0 : 0.0;
+      else if (kind == AGD_GRAD_HINGE) { y = (m > 0) ? 1.0 : 0.0; if (u < 0.05) y = 1.0 - y; }
+      else {
+        uint32_t e[4];
+        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)(i >> 32), 0u, 4u, e);
+        y = m + 0.1 * ((double)irwin_hall4(e[0], e[1]) * (1.7320508075688772 / 65536.0));
+      }
+      labels[r] = y;
+    }
+  }
+}
+
 template <typename D, typename S>
 __global__ void __launch_bounds__(256) convert_rows_kernel(D *dst, const S *src, long long rows, int d, long long ld) {
   const long long total = rows * (long long)d;
@@ -116,6 +168,10 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(D *dst, const S *src,
     const int j = (int)(q - r * d);
     dst[q] = convert_elem<D, S>(src[r * ld + j]);
   }
+}
+
+__global__ void csr_shift_rowptr_kernel(long long *dst, const long long *src, long long n, long long shift) {
+  for (long long q = blockIdx.x * 256LL + threadIdx.x; q < n; q += (long long)gridDim.x * 256LL) dst[q] = src[q] + shift;
 }
 
 inline unsigned grid_for(long long total) {
@@ -155,6 +211,29 @@ cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_t
     synth_labels_kernel<float><<<grid, 256, 0, st>>>((const float *)X, w_true, labels, seed, kind, row0, rows, d);
   else
     synth_labels_kernel<double><<<grid, 256, 0, st>>>((const double *)X, w_true, labels, seed, kind, row0, rows, d);
+  return cudaGetLastError();
+}
+
+cudaError_t csr_shift_rowptr_launch(int64_t *dst, const int64_t *src, int64_t n, int64_t shift, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  csr_shift_rowptr_kernel<<<grid_for(n), 256, 0, st>>>((long long *)dst, (const long long *)src, n, shift);
+  return cudaGetLastError();
+}
+
+cudaError_t synth_csr_launch(int64_t *rowptr, int32_t *idx, void *val, int elem_bytes, const double *w_true,
+                             double *labels, uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, int32_t k,
+                             cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const unsigned g1 = grid_for(rows * (long long)k), g2 = grid_for(rows * 32);
+  if (elem_bytes == 4) {
+    synth_csr_kernel<float><<<g1, 256, 0, st>>>((long long *)rowptr, idx, (float *)val, seed, row0, rows, d, k);
+    synth_csr_labels_kernel<float><<<g2, 256, 0, st>>>((const long long *)rowptr, idx, (const float *)val, w_true, labels,
+                                                       seed, kind, row0, rows);
+  } else {
+    synth_csr_kernel<double><<<g1, 256, 0, st>>>((long long *)rowptr, idx, (double *)val, seed, row0, rows, d, k);
+    synth_csr_labels_kernel<double><<<g2, 256, 0, st>>>((const long long *)rowptr, idx, (const double *)val, w_true,
+                                                        labels, seed, kind, row0, rows);
+  }
   return cudaGetLastError();
 }
 

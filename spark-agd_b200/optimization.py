@@ -159,6 +159,16 @@ class Context:
         return ds
 
 
+def _synthetic_csr(ctx, total_rows, d, nnz_per_row, gradient, seed=42, store="f32"):
+    ds = DeviceDataset(ctx)
+    N.check(N.lib().agd_generate_csr(ds.h, total_rows, d, nnz_per_row, _STORE[store], seed, _grad_kind(gradient)), ds.h)
+    ds.total_rows = total_rows
+    return ds
+
+
+Context.synthetic_csr = _synthetic_csr
+
+
 class DeviceDataset:
     """RDD[(Double, Vector)] stand-in: row shards pinned in HBM for the lifetime of the object."""
 
@@ -226,6 +236,16 @@ class DeviceDataset:
         y = np.empty(rows, dtype=np.float64)
         N.check(N.lib().agd_get_rows(self.h, dev, row0, rows, _ptr(X), _ptr(y)), self.h)
         return X, y
+
+    def get_csr_rows(self, dev: int, row0: int, rows: int, nnz_capacity: int, dtype=np.float32):
+        rowptr = np.empty(rows + 1, dtype=np.int64)
+        idx = np.empty(nnz_capacity, dtype=np.int32)
+        val = np.empty(nnz_capacity, dtype=dtype)
+        y = np.empty(rows, dtype=np.float64)
+        N.check(N.lib().agd_get_csr_rows(self.h, dev, row0, rows, _ptr(rowptr), _ptr(idx), _ptr(val), nnz_capacity,
+                                         _ptr(y)), self.h)
+        n = int(rowptr[-1])
+        return rowptr, idx[:n], val[:n], y
 
     def set_option(self, key: str, value) -> None:
         N.check(N.lib().agd_set_option(self.h, key.encode(), str(value).encode()), self.h)

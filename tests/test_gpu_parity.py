@@ -241,6 +241,32 @@ def test_csr_smooth_matches_oracle(agd, ctx, oracle, grad, store):
     ds.close()
 
 
+def test_csr_appended_partitions_and_generator(agd, ctx, oracle):
+    """Several SparseVector partitions appended to one GPU == one load; the on-device CSR generator ==
+    its CPU twin; a whole hinge + L2 run on CSR rows == the oracle (BASELINE configs[2] in miniature)."""
+    n, d, k, seed = 6000, 4096, 16, 11
+    rp, ix, va = oracle.synth_csr_f32(seed, 0, n, d, k)
+    gen = ctx.synthetic_csr(n, d, k, agd.HingeGradient(), seed=seed, store="f32")
+    grp, gix, gva, y = gen.get_csr_rows(0, 0, n, n * k)
+    assert np.array_equal(grp, rp) and np.array_equal(gix, ix) and np.array_equal(gva, va)
+    assert np.all(np.diff(ix.reshape(n, k), axis=1) > 0)            # strictly increasing column ids per row
+    many = agd.DeviceDataset(ctx)
+    for lo, hi in [(0, 1000), (1000, 1001), (1001, 4000), (4000, 6000)]:
+        many.load_csr(y[lo:hi], rp[lo:hi + 1] - rp[lo], ix[rp[lo]:rp[hi]], va[rp[lo]:rp[hi]], d, store="f32")
+    w = np.random.default_rng(1).standard_normal(d) * 0.1
+    a, b = gen.smooth(agd.HingeGradient(), w), many.smooth(agd.HingeGradient(), w)
+    assert a[2] == b[2] == n
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-14)
+    assert rel_err(a[1], b[1]) < 1e-13                               # RED.ADD order differs run to run
+    w0 = np.zeros(d)
+    wg, hist, st = agd.run_with_stats(many, agd.HingeGradient(), agd.SquaredL2Updater(), 0.0, 8, 0.1, w0)
+    ref = oracle.agd_run(oracle.Data(y, csr=(rp, ix, va), d=d), "hinge", "squared_l2", w0, convergence_tol=0.0,
+                         num_iterations=8, reg_param=0.1)
+    np.testing.assert_allclose(hist, ref.loss_history, rtol=1e-10)
+    assert rel_err(wg, ref.weights) < 1e-8
+    gen.close(); many.close()
+
+
 # ------------------------------------------------------------------ applyProjector (K3 prox)
 @pytest.mark.parametrize("upd", UPDS)
 @pytest.mark.parametrize("d", [2, 100, 1024, 70001])
