@@ -106,7 +106,7 @@ struct agd_handle {
   int32_t d = 0;
   int world = 1, first_rank = 0;
   bool comm_ready = false;
-  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised
+  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised, 4 tcgen05 (bf16)
   int ring_stages = 0;
   int tune_rows = 0, tune_ctas = 0;
   int k1_diag = 0;
@@ -287,6 +287,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     bool ring = k1_ring_supported(d, eb) != 0;
     if (h->k1_variant == 2) ring = false;
     const bool ws = ring && h->k1_variant == 3;
+    const bool tc = k1_tc_supported(d, eb) && (h->k1_variant == 0 || h->k1_variant == 4);
+    if (h->k1_variant == 4 && !tc) return fail(h, "tcgen05 kernel needs bf16 storage with d %% 128 == 0 and d <= 4096 (d=%d)", d);
     if ((h->k1_variant == 1 || h->k1_variant == 3) && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
     int max_blocks = k1_max_blocks(D.sm_count);
     if (!ring) {  // generic: bound the slab memory for very wide rows
@@ -297,7 +299,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     a.slabs = D.slabs;
     int blocks = 0;
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-    if (ws) CK(k1_ws_launch(a, eb, D.sm_count, &blocks, D.st));
+    if (tc) CK(k1_tc_launch(a, D.sm_count, &blocks, D.st));
+    else if (ws) CK(k1_ws_launch(a, eb, D.sm_count, &blocks, D.st));
     else if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
     else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
@@ -782,7 +785,8 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
     else if (!strcmp(value, "ring")) h->k1_variant = 1;
     else if (!strcmp(value, "generic")) h->k1_variant = 2;
     else if (!strcmp(value, "ws")) h->k1_variant = 3;
-    else return fail(h, "k1_variant must be auto|ring|generic|ws");
+    else if (!strcmp(value, "tc")) h->k1_variant = 4;
+    else return fail(h, "k1_variant must be auto|ring|generic|ws|tc");
     return 0;
   }
   if (!strcmp(key, "ring_stages")) { h->ring_stages = atoi(value); return 0; }

@@ -30,6 +30,9 @@ cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blo
 cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
                               cudaStream_t st);
 int k1_max_blocks(int sm_count);
+// bf16 shards: margins on CUDA cores, X^T r on tcgen05 (k1_tc.cu); d % 128 == 0, d <= 4096
+int k1_tc_supported(int32_t d, int elem_bytes);
+cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStream_t st);
 // out[c] = sum_b slabs[b][c] for c <= d ; out[d+1] = rows   (fixed order => deterministic)
 cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st);
 

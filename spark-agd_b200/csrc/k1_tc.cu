@@ -1,0 +1,379 @@
+// k1_tc.cu -- K1 for bf16-stored dense shards: margins on the CUDA cores, X^T r on tcgen05 (sm_100a).
+//
+// north_star's split for the bf16 configuration: the row tile is brought in ONCE by TMA tensor copies
+// (128B swizzle) and used twice without ever being widened into registers:
+//   phase 1 (CUDA cores, fp64): m_i = x_i . w  -- 256 consumer threads stream the 16-row tile out of
+//           shared memory, widen bf16 -> fp64 on the fly and FMA into 4 row accumulators per thread;
+//           nothing is retained, so the loop runs at streaming speed;
+//   scalar  (1 dedicated warp): margins -> loss', loss (k1_device.cuh); r_i = loss'_i is split into three
+//           bf16 pieces (hi / mid / lo, 24 mantissa bits) that form the B operand [N=16 x K=16 rows];
+//   phase 2 (tcgen05, fp32 in TMEM): D[c] (128 features x 16) += A (X^T chunk, MN-major view of the SAME
+//           swizzled tile) * B, one UTCHMMA per 128-feature chunk, issued by a single thread;
+//           every kFlush tiles the accumulators are read back (tcgen05.ld) and added into fp64 registers,
+//           so fp32 only ever holds sums over kFlush*16 rows.
+// Roles: warps 0-7 consumers (0-3 also own the fp64 gradient and flush TMEM), warp 8 TMA producer,
+// warp 9 MMA issuer, warp 10 scalar.  Shared-memory ring of 16 KB groups (8 blocks of [16 rows][64
+// features]); a group is released by the tcgen05.commit that follows the MMAs reading it.
+// Accuracy: margins and losses are fp64-exact like the other kernels; the gradient carries the bf16x3
+// split (2^-24) and fp32 partial sums, i.e. ~1e-7 relative (tests/test_gpu_parity.py states the bound).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agd_common.cuh"
+#include "k1_device.cuh"
+
+namespace agd {
+
+namespace {
+
+constexpr int kKR = 16;            // rows per tile = K of one MMA
+constexpr int kConsumers = 256;
+constexpr int kThreads = kConsumers + 96;  // + producer, MMA issuer, scalar warps
+constexpr int kFlush = 8;          // tiles between TMEM -> fp64 flushes (128 rows of fp32 accumulation)
+constexpr int kBlockBytes = kKR * 128;     // one [16 rows][64 features] swizzled block
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct TcLayout {
+  uint32_t ring_off, w_off, b2_off, partial_off, bars_off, tmem_off, total;
+};
+__host__ __device__ inline TcLayout tc_layout(int ring_groups, int group_bytes, int d) {
+  TcLayout L;
+  L.ring_off = 0;
+  L.w_off = (uint32_t)ring_groups * group_bytes;
+  L.b2_off = L.w_off + (uint32_t)d * 8;
+  L.partial_off = L.b2_off + 2 * 512;
+  L.bars_off = L.partial_off + 2 * kKR * 2 * 8;
+  L.tmem_off = L.bars_off + (2 * (uint32_t)ring_groups + 8) * 8;
+  L.total = L.tmem_off + 16;
+  return L;
+}
+
+struct TcArgs {
+  const double *labels;
+  const double *w;
+  double *slabs;
+  long long rows;
+  int d, kind, slab_stride;
+  int gb;           // 64-feature blocks per ring group (<= 8)
+  int ngt;          // groups per tile = d / (64 * gb)
+  int ring_groups;  // ring capacity in groups
+  int tmem_cols;    // power of two >= max(32, d / 8)
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const long long ntiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int group_bytes = a.gb * kBlockBytes;
+  const TcLayout L = tc_layout(a.ring_groups, group_bytes, a.d);
+  double *w_s = reinterpret_cast<double *>(smem + L.w_off);
+  unsigned char *b2 = smem + L.b2_off;                                       // [2][512 B]
+  double *partial = reinterpret_cast<double *>(smem + L.partial_off);         // [2][16 rows][2]
+  const uint32_t bars = smem_u32(smem + L.bars_off);
+  const int RG = a.ring_groups;
+  // full[g] = bars + 8g ; empty[g] = bars + 8(RG+g) ; then wbar, b2_full[2], b2_empty[2], tile_done, flush_done
+  const uint32_t wbar = bars + 16u * RG, b2_full = wbar + 8, b2_empty = b2_full + 16, tile_done = b2_empty + 16,
+                 flush_done = tile_done + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L.tmem_off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int nch = a.d / 128;
+  double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
+
+  if (tid == 0) {
+    for (int g = 0; g < RG; ++g) {
+      mbar_init(bars + 8u * g, 1);
+      mbar_init(bars + 8u * (RG + g), 1);
+    }
+    mbar_init(wbar, 1);
+    mbar_init(b2_full, 1); mbar_init(b2_full + 8, 1);
+    mbar_init(b2_empty, 1); mbar_init(b2_empty + 8, 1);
+    mbar_init(tile_done, 1);
+    mbar_init(flush_done, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // B operand rows 3..15 (unused N columns) stay zero for the whole kernel
+  for (int i = tid; i < 2 * 512 / 4; i += kThreads) reinterpret_cast<uint32_t *>(b2)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
+      tma_bulk_g2s(smem_u32(w_s), a.w, (uint32_t)a.d * 8u, wbar);
+      long long gcount = 0;
+      for (long long k = 0; k < my_tiles; ++k) {
+        const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * kKR;
+        for (int gi = 0; gi < a.ngt; ++gi, ++gcount) {
+          const int slot = (int)(gcount % RG);
+          const long long use = gcount / RG;
+          if (use > 0) mbar_wait(bars + 8u * (RG + slot), (uint32_t)((use - 1) & 1));
+          const uint32_t full = bars + 8u * slot;
+          mbar_expect_tx(full, (uint32_t)group_bytes);  // rows past the shard are zero-filled by TMA
+          for (int b = 0; b < a.gb; ++b)
+            tma_tile_2d(smem_u32(smem + (size_t)slot * group_bytes + b * kBlockBytes), &tmap, (gi * a.gb + b) * 64, (int)row0, full);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instr desc: D=F32, A=B=BF16, A MN-major, B K-major, N=16, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+      long long gcount = 0;
+      uint32_t flush_parity = 0;
+      for (long long k = 0; k < my_tiles; ++k) {
+        const int bb = (int)(k & 1);
+        mbar_wait(b2_full + 8u * bb, (uint32_t)((k >> 1) & 1));
+        const bool fresh = (k % kFlush) == 0;  // accumulators were just flushed (or never written)
+        if (fresh && k > 0) { mbar_wait(flush_done, flush_parity); flush_parity ^= 1u; }
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t bdesc = (uint64_t)((smem_u32(b2 + bb * 512) & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) |
+                               ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+        for (int gi = 0; gi < a.ngt; ++gi, ++gcount) {
+          const int slot = (int)(gcount % RG);
+          for (int cc = 0; cc < a.gb / 2; ++cc) {
+            const uint32_t a_addr = smem_u32(smem + (size_t)slot * group_bytes + (2 * cc) * kBlockBytes);
+            const uint64_t adesc = (uint64_t)((a_addr & 0x3FFFF) >> 4) | ((uint64_t)(kBlockBytes >> 4) << 16) |
+                                   ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+            const uint32_t taddr = tmem_base + (uint32_t)(gi * (a.gb / 2) + cc) * 16u;
+            const uint32_t acc = fresh ? 0u : 1u;
+            asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(taddr),
+                         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+                         : "memory");
+          }
+          umma_commit(bars + 8u * (RG + slot));  // the group may be refilled once these MMAs have read it
+        }
+        umma_commit(b2_empty + 8u * bb);
+        if (((k + 1) % kFlush) == 0 || k + 1 == my_tiles) umma_commit(tile_done);
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== scalar warp =====================
+    double lossacc = 0.0;
+    double ynext = 0.0;
+    if (lane < kKR) {
+      const long long r = (long long)blockIdx.x * kKR + lane;
+      if (r < a.rows) ynext = a.labels[r];
+    }
+    for (long long k = 0; k < my_tiles; ++k) {
+      const int bb = (int)(k & 1);
+      const long long tile = blockIdx.x + k * (long long)gridDim.x;
+      const long long left = a.rows - tile * kKR;
+      const int rv = left < kKR ? (int)left : kKR;
+      const double ylab = ynext;
+      if (lane < kKR) {
+        const long long r = (tile + gridDim.x) * kKR + lane;
+        if (r < a.rows) ynext = a.labels[r];
+      }
+      named_sync(1 + bb, kConsumers + 32);                     // partial dots of tile k are in shared memory
+      double mult = 0.0;
+      if (lane < kKR) {
+        const double m = partial[(bb * kKR + lane) * 2] + partial[(bb * kKR + lane) * 2 + 1];
+        double mu, loss;
+        loss_eval(a.kind, m, ylab, mu, loss);
+        if (lane < rv) { mult = mu; lossacc += loss; }
+      }
+      named_arrive(3 + bb, kConsumers + 32);                   // partial[bb] may be overwritten
+      if (k >= 2) mbar_wait(b2_empty + 8u * bb, (uint32_t)(((k >> 1) - 1) & 1));  // MMAs of tile k-2 have read b2[bb]
+      if (lane < kKR) {
+        // r_i -> three bf16 pieces; element (n, row) of the K-major B operand
+        const __nv_bfloat16 hi = __double2bfloat16(mult);
+        const double r1 = mult - (double)__bfloat162float(hi);
+        const __nv_bfloat16 mid = __double2bfloat16(r1);
+        const double r2 = r1 - (double)__bfloat162float(mid);
+        const __nv_bfloat16 lo = __double2bfloat16(r2);
+        unsigned char *base = b2 + bb * 512 + (lane / 8) * 128 + (lane % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(base + 0 * 16) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(base + 1 * 16) = mid;
+        *reinterpret_cast<__nv_bfloat16 *>(base + 2 * 16) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b2_full + 8u * bb);
+    }
+    for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+    if (lane == 0) slab[a.d] = lossacc;
+  } else {
+    // ===================== consumers: phase 1 in fp64, flush of the TMEM accumulators =====================
+    const int rq = tid >> 6;        // rows rq, rq+4, rq+8, rq+12
+    const int vv = tid & 63;        // 16-byte vector within the group row
+    mbar_wait(wbar, 0);
+    double gacc[32];                // warps 0-3: feature (c*128 + 32*warp + lane), c < d/128
+#pragma unroll
+    for (int c = 0; c < 32; ++c) gacc[c] = 0.0;
+    long long gcount = 0;
+    uint32_t done_parity = 0;
+    for (long long k = 0; k < my_tiles; ++k) {
+      const int bb = (int)(k & 1);
+      double p[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int gi = 0; gi < a.ngt; ++gi, ++gcount) {
+        const int slot = (int)(gcount % RG);
+        mbar_wait(bars + 8u * slot, (uint32_t)((gcount / RG) & 1));
+        if (vv < a.gb * 8) {
+          const int blk = vv >> 3, ch = vv & 7;
+          const double *wp = w_s + ((size_t)(gi * a.gb + blk) * 64 + ch * 8);
+          double wv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) wv[e] = wp[e];
+          const unsigned char *gbase = smem + (size_t)slot * group_bytes + blk * kBlockBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = rq + 4 * j;
+            const uint4 raw = *reinterpret_cast<const uint4 *>(gbase + row * 128 + ((ch ^ (row & 7)) << 4));
+            const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              p[j] = fma((double)__uint_as_float(wds[q] << 16), wv[2 * q], p[j]);
+              p[j] = fma((double)__uint_as_float(wds[q] & 0xffff0000u), wv[2 * q + 1], p[j]);
+            }
+          }
+        }
+      }
+      const double tot = warp_rows_reduce<4>(p, lane);        // lanes 8j..8j+7 hold row rq + 4j
+      if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
+      if ((lane & 7) == 0) partial[(bb * kKR + rq + 4 * (lane >> 3)) * 2 + (warp & 1)] = tot;
+      named_arrive(1 + bb, kConsumers + 32);
+
+      if (((k + 1) % kFlush) == 0 || k + 1 == my_tiles) {
+        // flush: wait for every MMA issued so far, add the fp32 tile sums into the fp64 gradient
+        if (warp < 4) {
+          mbar_wait(tile_done, done_parity);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c < nch) {
+              uint32_t v0, v1, v2, v3;
+              const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c * 16u;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                           : "r"(taddr));
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              gacc[c] += ((double)__uint_as_float(v0) + (double)__uint_as_float(v1)) + (double)__uint_as_float(v2);
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(flush_done);
+        }
+        done_parity ^= 1u;
+      }
+    }
+    if (warp < 4) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < nch) slab[c * 128 + warp * 32 + lane] = gacc[c];
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+int k1_tc_supported(int32_t d, int elem_bytes) { return elem_bytes == 2 && d >= 128 && d <= 4096 && d % 128 == 0; }
+
+cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStream_t st) {
+  if (!k1_tc_supported(a.d, 2)) return cudaErrorInvalidValue;
+  if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) return e != cudaSuccess ? e : cudaErrorUnknown;
+    encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.d, (cuuint64_t)a.rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)a.d * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)kKR};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(a.X), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  TcArgs t;
+  t.labels = a.labels; t.w = a.w; t.slabs = a.slabs; t.rows = a.rows; t.d = a.d; t.kind = a.kind;
+  t.slab_stride = a.slab_stride;
+  const int nblk = a.d / 64;
+  t.gb = nblk < 8 ? nblk : 8;
+  t.ngt = nblk / t.gb;
+  const int group_bytes = t.gb * kBlockBytes;
+  int ring = a.stages > 0 ? a.stages : 16;
+  const uint32_t budget = 227u * 1024u - 2048u;
+  while (ring > 2 && tc_layout(ring, group_bytes, a.d).total + 1024 > budget) --ring;
+  if (ring < t.ngt + 1) ring = t.ngt + 1;  // at least one tile and a bit
+  t.ring_groups = ring;
+  int cols = 32;
+  while (cols < a.d / 8) cols <<= 1;
+  t.tmem_cols = cols;
+  const TcLayout L = tc_layout(ring, group_bytes, a.d);
+  cudaError_t e = cudaFuncSetAttribute(k1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (a.rows + kKR - 1) / kKR;
+  long long grid = sm_count;
+  if (grid > ntiles) grid = ntiles;
+  *blocks_out = (int)grid;
+  k1_tc_kernel<<<(unsigned)grid, kThreads, L.total + 1024, st>>>(tmap, t, ntiles);
+  return cudaGetLastError();
+}
+
+}  // namespace agd
