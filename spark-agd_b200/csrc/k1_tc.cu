@@ -11,8 +11,8 @@
 //           swizzled tile) * B, one UTCHMMA per 128-feature chunk, issued by a single thread;
 //           every kFlush tiles the accumulators are read back (tcgen05.ld) and added into fp64 registers,
 //           so fp32 only ever holds sums over kFlush*16 rows.
-// Roles: warps 0-7 consumers (0-3 also own the fp64 gradient and flush TMEM), warp 8 TMA producer,
-// warp 9 MMA issuer, warp 10 scalar.  Shared-memory ring of 16 KB groups (8 blocks of [16 rows][64
+// Roles: warps 0-15 consumers, warp 16 TMA producer, warp 17 MMA issuer, warp 18 scalar, warps 20-23 own the fp64
+// gradient and flush TMEM; setmaxnreg moves registers from the consumers/aux warps to the flush warpgroup.  Shared-memory ring of 16 KB groups (8 blocks of [16 rows][64
 // features]); a group is released by the tcgen05.commit that follows the MMAs reading it.
 // Accuracy: margins and losses are fp64-exact like the other kernels; the gradient carries the bf16x3
 // split (2^-24) and fp32 partial sums, i.e. ~1e-7 relative (tests/test_gpu_parity.py states the bound).
@@ -29,8 +29,9 @@ namespace agd {
 namespace {
 
 constexpr int kKR = 16;            // rows per tile = K of one MMA
-constexpr int kConsumers = 256;
-constexpr int kThreads = kConsumers + 96;  // + producer, MMA issuer, scalar warps
+constexpr int kConsumers = 512;             // warpgroups 0-3
+constexpr int kThreads = kConsumers + 256;  // + warpgroup 4 (producer, MMA issuer, scalar, idle) + warpgroup 5 (flush)
+constexpr int kRegsConsumer = 64, kRegsAux = 56, kRegsFlush = 112;  // setmaxnreg: 80 at launch (768 threads)
 constexpr int kFlush = 8;          // tiles between TMEM -> fp64 flushes (128 rows of fp32 accumulation)
 constexpr int kBlockBytes = kKR * 128;     // one [16 rows][64 features] swizzled block
 
@@ -145,18 +146,21 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp >= 16 && warp < 20) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
+   if (warp == 16) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
       tma_bulk_g2s(smem_u32(w_s), a.w, (uint32_t)a.d * 8u, wbar);
-      long long gcount = 0;
+      int slot = -1;
+      uint32_t epar = 0;   // parity of the PREVIOUS use of a slot's empty barrier
+      bool wrapped = false;
       for (long long k = 0; k < my_tiles; ++k) {
         const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * kKR;
-        for (int gi = 0; gi < a.ngt; ++gi, ++gcount) {
-          const int slot = (int)(gcount % RG);
-          const long long use = gcount / RG;
-          if (use > 0) mbar_wait(bars + 8u * (RG + slot), (uint32_t)((use - 1) & 1));
+        for (int gi = 0; gi < a.ngt; ++gi) {
+          if (++slot == RG) { slot = 0; if (wrapped) epar ^= 1u; wrapped = true; }
+          if (wrapped) mbar_wait(bars + 8u * (RG + slot), epar);
           const uint32_t full = bars + 8u * slot;
           mbar_expect_tx(full, (uint32_t)group_bytes);  // rows past the shard are zero-filled by TMA
           for (int b = 0; b < a.gb; ++b)
@@ -164,12 +168,12 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
         }
       }
     }
-  } else if (warp == 9) {
+   } else if (warp == 17) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instr desc: D=F32, A=B=BF16, A MN-major, B K-major, N=16, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-      long long gcount = 0;
+      int slot = -1;
       uint32_t flush_parity = 0;
       for (long long k = 0; k < my_tiles; ++k) {
         const int bb = (int)(k & 1);
@@ -179,8 +183,8 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint64_t bdesc = (uint64_t)((smem_u32(b2 + bb * 512) & 0x3FFFF) >> 4) | ((uint64_t)(128 >> 4) << 16) |
                                ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
-        for (int gi = 0; gi < a.ngt; ++gi, ++gcount) {
-          const int slot = (int)(gcount % RG);
+        for (int gi = 0; gi < a.ngt; ++gi) {
+          if (++slot == RG) slot = 0;
           for (int cc = 0; cc < a.gb / 2; ++cc) {
             const uint32_t a_addr = smem_u32(smem + (size_t)slot * group_bytes + (2 * cc) * kBlockBytes);
             const uint64_t adesc = (uint64_t)((a_addr & 0x3FFFF) >> 4) | ((uint64_t)(kBlockBytes >> 4) << 16) |
@@ -197,7 +201,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
         if (((k + 1) % kFlush) == 0 || k + 1 == my_tiles) umma_commit(tile_done);
       }
     }
-  } else if (warp == 10) {
+   } else if (warp == 18) {
     // ===================== scalar warp =====================
     double lossacc = 0.0;
     double ynext = 0.0;
@@ -243,75 +247,93 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
     }
     for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
     if (lane == 0) slab[a.d] = lossacc;
-  } else {
-    // ===================== consumers: phase 1 in fp64, flush of the TMEM accumulators =====================
-    const int rq = tid >> 6;        // rows rq, rq+4, rq+8, rq+12
-    const int vv = tid & 63;        // 16-byte vector within the group row
-    mbar_wait(wbar, 0);
-    double gacc[32];                // warps 0-3: feature (c*128 + 32*warp + lane), c < d/128
+   }
+  } else if (warp >= 20) {
+    // ===================== flush warpgroup: owns the fp64 gradient, drains TMEM every kFlush tiles ==========
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsFlush));
+    const int fw = warp - 20;       // TMEM lanes 32*fw .. 32*fw+31
+    double gacc[32];                // feature (c*128 + 32*fw + lane), c < d/128
 #pragma unroll
     for (int c = 0; c < 32; ++c) gacc[c] = 0.0;
-    long long gcount = 0;
     uint32_t done_parity = 0;
     for (long long k = 0; k < my_tiles; ++k) {
-      const int bb = (int)(k & 1);
-      double p[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int gi = 0; gi < a.ngt; ++gi, ++gcount) {
-        const int slot = (int)(gcount % RG);
-        mbar_wait(bars + 8u * slot, (uint32_t)((gcount / RG) & 1));
-        if (vv < a.gb * 8) {
-          const int blk = vv >> 3, ch = vv & 7;
-          const double *wp = w_s + ((size_t)(gi * a.gb + blk) * 64 + ch * 8);
-          double wv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) wv[e] = wp[e];
-          const unsigned char *gbase = smem + (size_t)slot * group_bytes + blk * kBlockBytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int row = rq + 4 * j;
-            const uint4 raw = *reinterpret_cast<const uint4 *>(gbase + row * 128 + ((ch ^ (row & 7)) << 4));
-            const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              p[j] = fma((double)__uint_as_float(wds[q] << 16), wv[2 * q], p[j]);
-              p[j] = fma((double)__uint_as_float(wds[q] & 0xffff0000u), wv[2 * q + 1], p[j]);
-            }
-          }
-        }
-      }
-      const double tot = warp_rows_reduce<4>(p, lane);        // lanes 8j..8j+7 hold row rq + 4j
-      if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
-      if ((lane & 7) == 0) partial[(bb * kKR + rq + 4 * (lane >> 3)) * 2 + (warp & 1)] = tot;
-      named_arrive(1 + bb, kConsumers + 32);
-
       if (((k + 1) % kFlush) == 0 || k + 1 == my_tiles) {
-        // flush: wait for every MMA issued so far, add the fp32 tile sums into the fp64 gradient
-        if (warp < 4) {
-          mbar_wait(tile_done, done_parity);
-          asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c < nch) {
-              uint32_t v0, v1, v2, v3;
-              const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c * 16u;
-              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                           : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                           : "r"(taddr));
-              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-              gacc[c] += ((double)__uint_as_float(v0) + (double)__uint_as_float(v1)) + (double)__uint_as_float(v2);
-            }
-          }
-          asm volatile("tcgen05.fence::before_thread_sync;");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(flush_done);
-        }
+        mbar_wait(tile_done, done_parity);
         done_parity ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < nch) {
+            uint32_t v0, v1, v2, v3;
+            const uint32_t taddr = tmem_base + ((uint32_t)(fw * 32) << 16) + (uint32_t)c * 16u;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            gacc[c] += ((double)__uint_as_float(v0) + (double)__uint_as_float(v1)) + (double)__uint_as_float(v2);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(flush_done);
       }
     }
-    if (warp < 4) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < nch) slab[c * 128 + warp * 32 + lane] = gacc[c];
+    for (int c = 0; c < 32; ++c)
+      if (c < nch) slab[c * 128 + fw * 32 + lane] = gacc[c];
+  } else {
+    // ===================== consumers: phase 1 in fp64, straight out of the swizzled tile =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
+    const int rq = tid >> 6;        // rows rq and rq + 8
+    const int vv = tid & 63;        // 16-byte vector within the group row
+    mbar_wait(wbar, 0);
+    int slot = -1;
+    uint32_t par = 1;               // ring slot and its mbarrier phase, kept incrementally
+    const int blk = vv >> 3, ch = vv & 7;
+    const bool active = vv < a.gb * 8;
+    const int sw = (lane >> 1) & 3;
+    const uint32_t x_off0 = (uint32_t)(blk * kBlockBytes + rq * 128 + ((ch ^ (rq & 7)) << 4));       // row rq
+    const uint32_t x_off1 = x_off0 + 8 * 128;                                                        // row rq + 8: same swizzle
+    for (long long k = 0; k < my_tiles; ++k) {
+      const int bb = (int)(k & 1);
+      double p0a = 0.0, p0b = 0.0, p1a = 0.0, p1b = 0.0;
+      const double *wp = w_s + (blk * 64 + ch * 8);
+      for (int gi = 0; gi < a.ngt; ++gi) {
+        if (++slot == RG) slot = 0;
+        if (slot == 0) par ^= 1u;
+        mbar_wait(bars + 8u * slot, par);
+        if (active) {
+          const unsigned char *gbase = smem + (uint32_t)slot * (uint32_t)group_bytes;
+          const uint4 r0 = *reinterpret_cast<const uint4 *>(gbase + x_off0);
+          const uint4 r1 = *reinterpret_cast<const uint4 *>(gbase + x_off1);
+          // w pairs are read in a lane-rotated order (unit j = i ^ sw) so that the 8 lanes of a quarter-warp
+          // touch 8 different 16-byte bank groups (a plain 64-byte lane stride is a 4-way conflict); the x
+          // words are rotated the same way -- a dot product does not care about the order of its terms
+          uint32_t w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
+          if (sw & 1) {
+            uint32_t t0 = w0[0]; w0[0] = w0[1]; w0[1] = t0; t0 = w0[2]; w0[2] = w0[3]; w0[3] = t0;
+            uint32_t t1 = w1[0]; w1[0] = w1[1]; w1[1] = t1; t1 = w1[2]; w1[2] = w1[3]; w1[3] = t1;
+          }
+          if (sw & 2) {
+            uint32_t t0 = w0[0]; w0[0] = w0[2]; w0[2] = t0; t0 = w0[1]; w0[1] = w0[3]; w0[3] = t0;
+            uint32_t t1 = w1[0]; w1[0] = w1[2]; w1[2] = t1; t1 = w1[1]; w1[1] = w1[3]; w1[3] = t1;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 wq = *reinterpret_cast<const double2 *>(wp + 2 * (q ^ sw));  // features 2j, 2j+1, j = q ^ sw
+            p0a = fma((double)__uint_as_float(w0[q] << 16), wq.x, p0a);
+            p0b = fma((double)__uint_as_float(w0[q] & 0xffff0000u), wq.y, p0b);
+            p1a = fma((double)__uint_as_float(w1[q] << 16), wq.x, p1a);
+            p1b = fma((double)__uint_as_float(w1[q] & 0xffff0000u), wq.y, p1b);
+          }
+        }
+        wp += a.gb * 64;
+      }
+      double p[2] = {p0a + p0b, p1a + p1b};
+      const double tot = warp_rows_reduce<2>(p, lane);        // lanes 0-15 hold row rq, lanes 16-31 row rq + 8
+      if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
+      if ((lane & 15) == 0) partial[(bb * kKR + rq + 8 * (lane >> 4)) * 2 + (warp & 1)] = tot;
+      named_arrive(1 + bb, kConsumers + 32);
     }
   }
 
