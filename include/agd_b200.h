@@ -154,6 +154,13 @@ int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_siz
                double reg_param, const double *w0, double *w_out, double *loss_hist, int32_t *n_hist,
                agd_stats *stats);
 
+/* The mini-batch form: iteration i uses the rows kept by `data.sample(false, miniBatchFraction, 42 + i)`, realised as a
+ * counter-based Bernoulli mask (Philox keyed by 42 + i and the global row index; Spark's own sampler is seeded per
+ * partition and is not reproducible across partitionings either).  fraction >= 1 is the full batch. */
+int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, double step_size, int32_t num_iterations,
+                         double reg_param, double mini_batch_fraction, const double *w0, double *w_out,
+                         double *loss_hist, int32_t *n_hist, agd_stats *stats);
+
 /* Kernel-variant override for experiments/benchmarks: name in {"auto","ring","generic"}. */
 int agd_set_option(agd_handle *h, const char *key, const char *value);
 

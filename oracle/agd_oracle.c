@@ -150,6 +150,7 @@ int oracle_smooth(const oracle_data *D, int grad_kind, const double *w, int part
     double l = 0.0;
     int64_t c = 0;
     for (int64_t i = lo; i < hi; ++i) {
+      if (D->sample_thresh && !oracle_row_selected(D->sample_seed, D->sample_thresh, i)) continue; /* data.sample(...) */
       l = l + gradient_compute(D, grad_kind, i, w, g);
       c = c + 1;
     }
@@ -402,6 +403,35 @@ static double fdlibm_log(double x) {
   }
   if (k == 0) return f - s * (f - R);
   return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+/* runMiniBatchSGD with miniBatchFraction < 1: iteration i folds the rows of data.sample(false, fraction, 42 + i),
+ * realised as the counter-based Bernoulli mask of oracle_row_selected; an empty sample skips the update. */
+int oracle_gd_run_minibatch(oracle_data *D, int grad_kind, int upd_kind, double step_size, int num_iterations,
+                            double reg_param, double fraction, int partitions, int threads, const double *w0,
+                            double *w_out, double *loss_hist, int32_t *n_hist) {
+  const int32_t d = D->d;
+  const size_t bytes = (size_t)d * sizeof(double);
+  double *w = malloc(bytes), *g = malloc(bytes), *wn = malloc(bytes), *zero = calloc((size_t)d, sizeof(double));
+  if (!w || !g || !wn || !zero) return -1;
+  memcpy(w, w0, bytes);
+  int nh = 0;
+  double reg_val = updater_compute(upd_kind, w, zero, 0.0, 1, reg_param, d, wn);
+  for (int i = 1; i <= num_iterations && D->n > 0; ++i) {
+    double mean_loss; int64_t cnt;
+    D->sample_seed = 42ull + (uint64_t)i;
+    D->sample_thresh = fraction >= 1.0 ? 0ull : (uint64_t)ldexp(fraction, 64);
+    oracle_smooth(D, grad_kind, w, partitions, threads, &mean_loss, g, &cnt);
+    D->sample_thresh = 0;
+    if (cnt <= 0) continue;
+    loss_hist[nh++] = mean_loss + reg_val;
+    reg_val = updater_compute(upd_kind, w, g, step_size, i, reg_param, d, wn);
+    memcpy(w, wn, bytes);
+  }
+  memcpy(w_out, w, bytes);
+  *n_hist = nh;
+  free(w); free(g); free(wn); free(zero);
+  return 0;
 }
 
 /* ---------- java.util.Random (48-bit LCG) ---------- */

@@ -26,6 +26,8 @@ typedef struct {
   const double *csr_val;      /* f64 values, or NULL when csr_val_f32 is set */
   const float *csr_val_f32;
   const double *labels;       /* n */
+  uint64_t sample_seed;       /* mini-batch mask of the current pass; sample_thresh == 0 keeps every row */
+  uint64_t sample_thresh;
 } oracle_data;
 
 /* The eight hyper-parameters of AGD.scala:44-51 + the treeAggregate shape. */
@@ -81,6 +83,10 @@ void oracle_synth_wtrue(uint64_t seed, int32_t d, double *w);
 void oracle_synth_labels(uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, const float *X,
                          const double *w_true, double *labels);
 
+int oracle_row_selected(uint64_t seed, uint64_t thresh, int64_t grow);
+int oracle_gd_run_minibatch(oracle_data *D, int grad_kind, int upd_kind, double step_size, int num_iterations,
+                            double reg_param, double fraction, int partitions, int threads, const double *w0,
+                            double *w_out, double *loss_hist, int32_t *n_hist);
 void oracle_synth_csr_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, int32_t k, int64_t *rowptr,
                           int32_t *idx, float *val);
 

@@ -34,7 +34,8 @@ class _Data(C.Structure):
     _fields_ = [("n", C.c_int64), ("d", C.c_int32), ("storage", C.c_int32),
                 ("Xd", C.c_void_p), ("Xf", C.c_void_p), ("ld", C.c_int64),
                 ("rowptr", C.c_void_p), ("csr_idx", C.c_void_p), ("csr_val", C.c_void_p),
-                ("csr_val_f32", C.c_void_p), ("labels", C.c_void_p)]
+                ("csr_val_f32", C.c_void_p), ("labels", C.c_void_p), ("sample_seed", C.c_uint64),
+                ("sample_thresh", C.c_uint64)]
 
 
 class _Params(C.Structure):
@@ -158,12 +159,20 @@ def agd_run(data: Data, gradient: str, updater: str, w0, *, convergence_tol=1e-4
 
 
 def gd_run(data: Data, gradient: str, updater: str, w0, *, step_size=1.0, num_iterations=100, reg_param=0.0,
-           partitions=2, threads=1):
-    """GradientDescent.runMiniBatchSGD with miniBatchFraction=1.0 (comparator of Suite.scala:78)."""
+           partitions=2, threads=1, mini_batch_fraction=1.0):
+    """GradientDescent.runMiniBatchSGD (comparator of Suite.scala:78); fraction < 1 uses the counter-based row mask."""
     w0 = np.ascontiguousarray(w0, dtype=np.float64)
     w = np.empty_like(w0)
     hist = np.empty(max(num_iterations, 1), dtype=np.float64)
     nh = C.c_int32()
+    if mini_batch_fraction < 1.0:
+        lib().oracle_gd_run_minibatch.restype = C.c_int
+        rc = lib().oracle_gd_run_minibatch(C.byref(data._s), GRAD[gradient], UPD[updater], C.c_double(step_size),
+                                           C.c_int(num_iterations), C.c_double(reg_param),
+                                           C.c_double(mini_batch_fraction), C.c_int(partitions), C.c_int(threads),
+                                           _p(w0), _p(w), _p(hist), C.byref(nh))
+        assert rc == 0
+        return w, hist[:nh.value].copy()
     rc = lib().oracle_gd_run(C.byref(data._s), GRAD[gradient], UPD[updater], C.c_double(step_size),
                              C.c_int(num_iterations), C.c_double(reg_param), C.c_int(partitions),
                              C.c_int(threads), _p(w0), _p(w), _p(hist), C.byref(nh))

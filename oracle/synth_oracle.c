@@ -128,3 +128,12 @@ void oracle_synth_csr_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, 
   }
   rowptr[rows] = rows * (int64_t)k;
 }
+
+/* Bernoulli row mask of the mini-batch GD comparator (spec: row_selected() in spark-agd_b200/csrc/k1_device.cuh):
+ * keep row `grow` iff the 64-bit Philox4x32-10 draw keyed by `seed`, counter (row_lo, row_hi, 0, 6) is < thresh. */
+int oracle_row_selected(uint64_t seed, uint64_t thresh, int64_t grow) {
+  if (thresh == 0) return 1;
+  uint32_t c[4] = {(uint32_t)grow, (uint32_t)((uint64_t)grow >> 32), 0u, 6u}, o[4];
+  philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), c, o);
+  return ((((uint64_t)o[0]) << 32) | o[1]) < thresh;
+}

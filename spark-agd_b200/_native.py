@@ -89,6 +89,8 @@ _SIGNATURES = {
                           C.POINTER(C.c_int32), C.POINTER(Stats)]),
     "agd_gd_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(Stats)]),
+    "agd_gd_run_minibatch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(Stats)]),
     "agd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
 }
 

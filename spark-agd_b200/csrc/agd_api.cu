@@ -97,6 +97,7 @@ struct Dev {
   std::vector<cudaEvent_t> ev_ar;  // all-reduce start/stop pairs
   size_t ev_ar_used = 0;
   std::mutex *mu = nullptr;
+  long long row_base = 0;          // global index of this shard's first row (for the sampling mask)
 };
 
 }  // namespace
@@ -110,6 +111,7 @@ struct agd_handle {
   int ring_stages = 0;
   int tune_rows = 0, tune_ctas = 0;
   int k1_diag = 0;
+  unsigned long long sample_seed = 0, sample_thresh = 0;  // mini-batch row mask of the current pass (0 = every row)
   std::string err;
   std::mutex mu;
   int64_t launches = 0;  // per device, current call
@@ -192,7 +194,7 @@ int ensure_vectors(agd_handle *h, Dev &D, int32_t d) {
 }
 
 int ensure_slabs(agd_handle *h, Dev &D, int blocks, int32_t d) {
-  const size_t need = (size_t)blocks * ((size_t)d + 1);
+  const size_t need = (size_t)blocks * ((size_t)d + 2);
   if (need <= D.slabs_doubles) return 0;
   CK(cudaSetDevice(D.ordinal));
   if (D.slabs) cudaFree(D.slabs);
@@ -274,6 +276,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
       K1CsrArgs a;
       a.rowptr = s.rowptr; a.idx = s.idx; a.val = s.val; a.labels = s.labels; a.w = w_of(D);
       a.gacc = D.acc; a.rows = s.rows; a.d = d; a.kind = kind;
+      a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base;
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
       CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
@@ -282,7 +285,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     }
     K1Args a;
     a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
-    a.stages = h->ring_stages; a.slab_stride = d + 1; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas;
+    a.stages = h->ring_stages; a.slab_stride = d + 2;
+    a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     bool ring = k1_ring_supported(d, eb) != 0;
     if (h->k1_variant == 2) ring = false;
@@ -292,7 +296,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     if ((h->k1_variant == 1 || h->k1_variant == 3) && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
     int max_blocks = k1_max_blocks(D.sm_count);
     if (!ring) {  // generic: bound the slab memory for very wide rows
-      const long long lim = (32LL << 20) / ((long long)d + 1);
+      const long long lim = (32LL << 20) / ((long long)d + 2);
       if (lim < max_blocks) max_blocks = lim < 1 ? 1 : (int)lim;
     }
     if (ensure_slabs(h, D, max_blocks, d)) return 1;
@@ -451,6 +455,7 @@ int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
   }
   nh->world = n_dev;
   nh->first_rank = 0;
+  for (int i = 0; i < n_dev; ++i) nh->devs[i].row_base = (long long)i << 40;  // loaded shards: one mask stream per rank
   *out = nh;
   if (n_dev > 1) {  // single-process owner of several GPUs: build the communicator now
     unsigned char id[128];
@@ -520,6 +525,7 @@ int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t
   h->world = world_ranks;
   h->first_rank = first_rank;
   h->comm_ready = true;
+  for (int i = 0; i < nd; ++i) h->devs[i].row_base = (long long)(first_rank + i) << 40;
   return 0;
 }
 
@@ -674,6 +680,7 @@ int agd_generate_csr(agd_handle *h, int64_t total_rows, int32_t d, int32_t nnz_p
     if (csr_reserve_locked(h, D, hi - lo, (hi - lo) * nnz_per_row, eb)) return 1;
     if (ensure_vectors(h, D, d)) return 1;
     CK(cudaSetDevice(D.ordinal));
+    D.row_base = lo;
     CK(synth_wtrue_launch(D.wtmp, seed, d, D.st));
     CK(synth_csr_launch(D.sh.rowptr, D.sh.idx, D.sh.val, eb, D.wtmp, D.sh.labels, seed, gradient, lo, hi - lo, d,
                         nnz_per_row, D.st));
@@ -741,6 +748,7 @@ int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dty
     if (reserve_locked(h, D, hi - lo, d, store_dtype)) return 1;
     if (ensure_vectors(h, D, d)) return 1;
     CK(cudaSetDevice(D.ordinal));
+    D.row_base = lo;
     CK(synth_dense_launch(D.sh.X, eb, seed, lo, hi - lo, d, D.st));
     CK(synth_wtrue_launch(D.wtmp, seed, d, D.st));
     CK(synth_labels_launch(D.sh.X, eb, D.wtmp, D.sh.labels, seed, gradient, lo, hi - lo, d, D.st));
@@ -992,7 +1000,15 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
 int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_size, int32_t num_iterations,
                double reg_param, const double *w0, double *w_out, double *loss_hist, int32_t *n_hist,
                agd_stats *stats) {
+  return agd_gd_run_minibatch(h, gradient, updater, step_size, num_iterations, reg_param, 1.0, w0, w_out, loss_hist,
+                              n_hist, stats);
+}
+
+int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, double step_size, int32_t num_iterations,
+                         double reg_param, double mini_batch_fraction, const double *w0, double *w_out,
+                         double *loss_hist, int32_t *n_hist, agd_stats *stats) {
   if (check_ready(h)) return 1;
+  if (!(mini_batch_fraction > 0.0)) return fail(h, "miniBatchFraction must be positive");
   if (gradient < 0 || gradient > AGD_GRAD_LEAST_SQUARES_HALF) return fail(h, "unknown gradient %d", gradient);
   if (updater < 0 || updater > AGD_UPD_L1) return fail(h, "unknown updater %d", updater);
   const auto t_begin = std::chrono::steady_clock::now();
@@ -1029,12 +1045,17 @@ int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_siz
   double reg_val = reg_value(updater, reg_param, sc[2], sc[5]);
   int nh = 0;
   for (int i = 1; i <= num_iterations; ++i) {
-    if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
+    // data.sample(false, miniBatchFraction, 42 + i): Bernoulli row mask keyed by the iteration
+    h->sample_seed = 42ull + (unsigned long long)i;
+    h->sample_thresh = mini_batch_fraction >= 1.0 ? 0ull : (unsigned long long)std::ldexp(mini_batch_fraction, 64);
+    const int rc_smooth = smooth_device(h, gradient, [](Dev &D) { return (const double *)D.x; }, true);
+    h->sample_thresh = 0ull;
+    if (rc_smooth) return 1;
     s.passes++;
     const double this_step = step_size / std::sqrt((double)i);
     if (prox_all(nullptr, this_step, true)) return 1;
     if (read_scalars(h, sc)) return 1;
-    if (!(sc[7] > 0)) break;  // miniBatchSize == 0: the reference logs a warning and skips the update
+    if (!(sc[7] > 0)) continue;  // miniBatchSize == 0: the reference logs a warning and skips the update
     loss_hist[nh++] = sc[6] / sc[7] + reg_val;
     reg_val = reg_value(updater, reg_param, sc[2], sc[5]);
     s.iterations = i;

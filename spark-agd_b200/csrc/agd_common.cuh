@@ -13,12 +13,14 @@ struct K1Args {
   const void *X;          // shard, row-major, ld == d, element type float or double
   const double *labels;   // rows (+ padding)
   const double *w;        // d doubles (device)
-  double *slabs;          // [grid][d + 1]: per-block column sums of loss' * x, then the loss sum
+  double *slabs;          // [grid][d + 2]: per-block column sums of loss' * x, the loss sum, the row count
   int64_t rows;           // rows in the shard
   int32_t d;
   int32_t kind;           // AGD_GRAD_*
   int32_t stages;         // smem ring depth
-  int32_t slab_stride;    // d + 1
+  int32_t slab_stride;    // d + 2
+  unsigned long long sample_seed, sample_thresh;  // Bernoulli row mask (thresh 0 = every row), see row_selected()
+  long long row_base;     // global index of the shard's first row
   int32_t tune_rows;      // 0 = default; rows per tile of the headline ring shape (4|8)
   int32_t tune_ctas;      // 0 = default; resident CTAs per SM (1|2|3)
 };
@@ -33,7 +35,7 @@ int k1_max_blocks(int sm_count);
 // bf16 shards: margins on CUDA cores, X^T r on tcgen05 (k1_tc.cu); d % 128 == 0, d <= 4096
 int k1_tc_supported(int32_t d, int elem_bytes);
 cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStream_t st);
-// out[c] = sum_b slabs[b][c] for c <= d ; out[d+1] = rows   (fixed order => deterministic)
+// out[c] = sum_b slabs[b][c] for c <= d + 1 (gradient sums, loss sum, row count; fixed order => deterministic)
 cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st);
 
 // CSR variant (k1_csr.cu)
@@ -47,6 +49,8 @@ struct K1CsrArgs {
   int64_t rows;
   int32_t d;
   int32_t kind;
+  unsigned long long sample_seed, sample_thresh;
+  long long row_base;
 };
 cudaError_t k1_csr_launch(const K1CsrArgs &a, int elem_bytes, int sm_count, cudaStream_t st);
 

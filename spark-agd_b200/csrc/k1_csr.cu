@@ -18,12 +18,12 @@ namespace {
 
 template <typename T>
 __global__ void __launch_bounds__(256) k1_csr_kernel(const K1CsrArgs a) {
-  __shared__ double red[8];
+  __shared__ double red[16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp_global = (blockIdx.x * 256LL + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * 256LL) >> 5;
   const T *val = reinterpret_cast<const T *>(a.val);
-  double lossacc = 0.0;
+  double lossacc = 0.0, cntacc = 0.0;
   for (long long r = warp_global; r < a.rows; r += nwarps) {
     const long long lo = a.rowptr[r], hi = a.rowptr[r + 1];
     double m = 0.0;
@@ -31,19 +31,24 @@ __global__ void __launch_bounds__(256) k1_csr_kernel(const K1CsrArgs a) {
     for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(0xffffffffu, m, off);
     double mult, loss;
     loss_eval(a.kind, m, a.labels[r], mult, loss);
+    if (!row_selected(a.sample_seed, a.sample_thresh, a.row_base + r)) { mult = 0.0; loss = 0.0; }
+    else if (lane == 0) cntacc += 1.0;
     if (lane == 0) lossacc += loss;
     if (mult != 0.0) {
       for (long long k = lo + lane; k < hi; k += 32) atomicAdd(&a.gacc[a.idx[k]], mult * (double)val[k]);
     }
   }
-  for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
-  if (lane == 0) red[warp] = lossacc;
+  for (int off = 16; off >= 1; off >>= 1) {
+    lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+    cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
+  }
+  if (lane == 0) { red[warp] = lossacc; red[8 + warp] = cntacc; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += red[w];
+    double s = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) { s += red[w]; c += red[8 + w]; }
     atomicAdd(&a.gacc[a.d], s);
-    if (blockIdx.x == 0) a.gacc[a.d + 1] = (double)a.rows;
+    atomicAdd(&a.gacc[a.d + 1], c);   // counts are small integers: exact in any order
   }
 }
 

@@ -175,7 +175,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       acc[v][e] = 0.0;
       acc2[v][e] = 0.0;
     }
-  double lossacc = 0.0;
+  double lossacc = 0.0, cntacc = 0.0;
 
   int k = 0, s = -1;
   uint32_t par = 1;
@@ -265,9 +265,10 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       const double m = ((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7]));
       double mult, loss;
       loss_eval(a.kind, m, ylab, mult, loss);
-      const bool valid = lane < rv;
+      const bool valid = lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + lane);
       mult_s[lane] = valid ? mult : 0.0;
       lossacc += valid ? loss : 0.0;
+      cntacc += valid ? 1.0 : 0.0;
     }
     __syncthreads();
 
@@ -321,13 +322,17 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       }
     }
   }
-  for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
-  if (lane == 0) red[warp] = lossacc;
+  for (int off = 16; off >= 1; off >>= 1) {
+    lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+    cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
+  }
+  if (lane == 0) { red[warp] = lossacc; red[8 + warp] = cntacc; }
   __syncthreads();
   if (tid == 0) {
-    double sacc = 0.0;
-    for (int wi = 0; wi < NW; ++wi) sacc += red[wi];
+    double sacc = 0.0, cacc = 0.0;
+    for (int wi = 0; wi < NW; ++wi) { sacc += red[wi]; cacc += red[8 + wi]; }
     slab[a.d] = sacc;
+    slab[a.d + 1] = cacc;
   }
 }
 
@@ -420,7 +425,7 @@ k1_ws_kernel(const K1Args a, const int nvec, const long long ntiles, const uint3
     }
    } else if (warp == NCW) {
     // ===================== scalar warp: margins -> loss', loss =====================
-    double lossacc = 0.0;
+    double lossacc = 0.0, cntacc = 0.0;
     double ynext = 0.0;
     if (lane < TR) {
       const long long r = (long long)blockIdx.x * TR + lane;
@@ -444,14 +449,18 @@ k1_ws_kernel(const K1Args a, const int nvec, const long long ntiles, const uint3
         for (int wi = 0; wi < WPG; ++wi) m += pp[wi];
         double mult, loss;
         loss_eval(a.kind, m, ylab, mult, loss);
-        const bool valid = lane < rv;
+        const bool valid = lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + tile * TR + lane);
         mult_s[b * kMaxTileRows + lane] = valid ? mult : 0.0;
         lossacc += valid ? loss : 0.0;
+        cntacc += valid ? 1.0 : 0.0;
       }
       named_arrive(3 + b, kWsConsumers + 32);
     }
-    for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
-    if (lane == 0) slab[a.d] = lossacc;
+    for (int off = 16; off >= 1; off >>= 1) {
+      lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+      cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
+    }
+    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; }
    }
     return;
   }
@@ -590,12 +599,12 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
   constexpr int R = 8;
   __shared__ double part[R][8];
   __shared__ double mult_s[R];
-  __shared__ double red[8];
+  __shared__ double red[16];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const T *X = reinterpret_cast<const T *>(a.X);
   double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
   for (int c = tid; c <= a.d; c += 256) slab[c] = 0.0;
-  double lossacc = 0.0;
+  double lossacc = 0.0, cntacc = 0.0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * R;
     const long long left = a.rows - row0;
@@ -617,7 +626,10 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
 #pragma unroll
       for (int wi = 0; wi < 8; ++wi) m += part[tid][wi];
       double mult = 0.0, loss = 0.0;
-      if (tid < rv) loss_eval(a.kind, m, a.labels[row0 + tid], mult, loss);
+      if (tid < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + tid)) {
+        loss_eval(a.kind, m, a.labels[row0 + tid], mult, loss);
+        cntacc += 1.0;
+      }
       mult_s[tid] = mult;
       lossacc += loss;
     }
@@ -630,18 +642,22 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
       slab[c] = sacc;
     }
   }
-  for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
-  if (lane == 0) red[warp] = lossacc;
+  for (int off = 16; off >= 1; off >>= 1) {
+    lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+    cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
+  }
+  if (lane == 0) { red[warp] = lossacc; red[8 + warp] = cntacc; }
   __syncthreads();
   if (tid == 0) {
-    double sacc = 0.0;
-    for (int wi = 0; wi < 8; ++wi) sacc += red[wi];
+    double sacc = 0.0, cacc = 0.0;
+    for (int wi = 0; wi < 8; ++wi) { sacc += red[wi]; cacc += red[8 + wi]; }
     slab[a.d] = sacc;
+    slab[a.d + 1] = cacc;
   }
 }
 
 // ---------------------------------------------------------------- slab reduction (combOp, AGD.scala:201-204)
-// out[c] = sum over slabs of column c, c <= d.  32 columns per block; 8 slab groups per block sum
+// out[c] = sum over slabs of column c, c <= d + 1 (gradient, loss sum, row count).  32 columns per block; 8 slab groups per block sum
 // strided subsets (slab b -> group b % 8) with 4 loads in flight, then group 0 adds the 8 group sums in
 // order: the summation tree is fixed, so the result is bit-reproducible.
 __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int d,
@@ -649,9 +665,9 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
   __shared__ double part[8][33];
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  const size_t stride = (size_t)d + 1;
+  const size_t stride = (size_t)d + 2;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  if (c <= d) {
+  if (c <= d + 1) {
     int b = grp;
     for (; b + 24 < blocks; b += 32) {
       const double v0 = slabs[(size_t)b * stride + c], v1 = slabs[(size_t)(b + 8) * stride + c],
@@ -662,13 +678,13 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
   }
   part[grp][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  if (grp == 0 && c <= d) {
+  if (grp == 0 && c <= d + 1) {
     double t = 0.0;
 #pragma unroll
     for (int gi = 0; gi < 8; ++gi) t += part[gi][cl];
     out[c] = t;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[d + 1] = (double)rows;
+  (void)rows;
 }
 
 struct RingShape { int tpr, v, r; };
@@ -856,7 +872,7 @@ cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int
 }
 
 cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st) {
-  const int grid = (d + 1 + 31) / 32;
+  const int grid = (d + 2 + 31) / 32;
   k1_reduce_kernel<<<grid, 256, 0, st>>>(slabs, blocks, d, (long long)rows, out);
   return cudaGetLastError();
 }

@@ -107,6 +107,25 @@ __device__ __forceinline__ void loss_eval(int kind, double m, double y, double &
   }
 }
 
+// Bernoulli row mask of the mini-batch form of runMiniBatchSGD (`data.sample(false, fraction, 42 + i)`):
+// row `grow` (global index) is kept iff the 64-bit Philox4x32-10 draw keyed by `seed`, counter (row, 0, 6) is
+// below `thresh` (= fraction * 2^64; thresh == 0 means "no sampling").  Counter-based, so the mask does not depend
+// on how rows are sharded over GPUs.  (Spark's own sampler is seeded per partition and is not reproducible either.)
+__device__ __forceinline__ bool row_selected(unsigned long long seed, unsigned long long thresh, long long grow) {
+  if (thresh == 0ull) return true;
+  uint32_t c0 = (uint32_t)grow, c1 = (uint32_t)((unsigned long long)grow >> 32), c2 = 0u, c3 = 6u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (((unsigned long long)c0 << 32) | c1) < thresh;
+}
+
 // Transpose-reduce R per-lane partials across a warp: afterwards every lane holds the warp total of
 // row (lane / (32/R)).  R/2 + R/4 + ... + 1 + log2(32/R) 64-bit shuffles instead of 5R.
 template <int R>

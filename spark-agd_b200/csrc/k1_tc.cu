@@ -97,6 +97,8 @@ struct TcArgs {
   double *slabs;
   long long rows;
   int d, kind, slab_stride;
+  unsigned long long sample_seed, sample_thresh;
+  long long row_base;
   int gb;           // 64-feature blocks per ring group (<= 8)
   int ngt;          // groups per tile = d / (64 * gb)
   int ring_groups;  // ring capacity in groups
@@ -203,7 +205,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
     }
    } else if (warp == 18) {
     // ===================== scalar warp =====================
-    double lossacc = 0.0;
+    double lossacc = 0.0, cntacc = 0.0;
     double ynext = 0.0;
     if (lane < kKR) {
       const long long r = (long long)blockIdx.x * kKR + lane;
@@ -225,7 +227,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
         const double m = partial[(bb * kKR + lane) * 2] + partial[(bb * kKR + lane) * 2 + 1];
         double mu, loss;
         loss_eval(a.kind, m, ylab, mu, loss);
-        if (lane < rv) { mult = mu; lossacc += loss; }
+        if (lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + tile * kKR + lane)) {
+          mult = mu; lossacc += loss; cntacc += 1.0;
+        }
       }
       named_arrive(3 + bb, kConsumers + 32);                   // partial[bb] may be overwritten
       if (k >= 2) mbar_wait(b2_empty + 8u * bb, (uint32_t)(((k >> 1) - 1) & 1));  // MMAs of tile k-2 have read b2[bb]
@@ -245,8 +249,11 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
       __syncwarp();
       if (lane == 0) mbar_arrive(b2_full + 8u * bb);
     }
-    for (int off = 16; off >= 1; off >>= 1) lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
-    if (lane == 0) slab[a.d] = lossacc;
+    for (int off = 16; off >= 1; off >>= 1) {
+      lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
+      cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
+    }
+    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; }
    }
   } else if (warp >= 20) {
     // ===================== flush warpgroup: owns the fp64 gradient, drains TMEM every kFlush tiles ==========
@@ -375,6 +382,7 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
   TcArgs t;
   t.labels = a.labels; t.w = a.w; t.slabs = a.slabs; t.rows = a.rows; t.d = a.d; t.kind = a.kind;
   t.slab_stride = a.slab_stride;
+  t.sample_seed = a.sample_seed; t.sample_thresh = a.sample_thresh; t.row_base = a.row_base;
   const int nblk = a.d / 64;
   t.gb = nblk < 8 ? nblk : 8;
   t.ngt = nblk / t.gb;

@@ -374,17 +374,16 @@ def run_with_stats(data: DeviceDataset, gradient, updater, convergenceTol, numIt
 
 class GradientDescent:
     """GradientDescent.runMiniBatchSGD [mllib-1.3.0], the comparator of Suite.scala:78,118,225
-    (miniBatchFraction must be 1.0: full batch, the only form the reference's tests use)."""
+    (miniBatchFraction < 1 samples rows with a counter-based Bernoulli mask keyed by 42 + i, see include/agd_b200.h)."""
 
     @staticmethod
     def runMiniBatchSGD(data: DeviceDataset, gradient: Gradient, updater: Updater, stepSize: float, numIterations: int,
                         regParam: float, miniBatchFraction: float, initialWeights):
-        if miniBatchFraction != 1.0:
-            raise NotImplementedError("only miniBatchFraction = 1.0 is implemented (SURVEY.md 8(f).1)")
         w0 = np.ascontiguousarray(initialWeights, dtype=np.float64)
         w = np.empty_like(w0)
         hist = np.empty(max(int(numIterations), 1), dtype=np.float64)
         nh, st = C.c_int32(), N.Stats()
-        N.check(N.lib().agd_gd_run(data.h, _grad_kind(gradient), _upd_kind(updater), stepSize, int(numIterations),
-                                   regParam, _ptr(w0), _ptr(w), _ptr(hist), C.byref(nh), C.byref(st)), data.h)
+        N.check(N.lib().agd_gd_run_minibatch(data.h, _grad_kind(gradient), _upd_kind(updater), stepSize,
+                                             int(numIterations), regParam, float(miniBatchFraction), _ptr(w0), _ptr(w),
+                                             _ptr(hist), C.byref(nh), C.byref(st)), data.h)
         return w, hist[:nh.value].copy()

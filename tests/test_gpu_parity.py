@@ -349,6 +349,31 @@ def test_suite_T1_T2_T4_on_gpu(agd, ctx, oracle, fixture_gd_input):
     data.close()
 
 
+@pytest.mark.parametrize("shape,store,variant", [((20000, 1024), "f32", "auto"), ((5000, 100), "f64", "auto"),
+                                                 ((9000, 512), "f32", "ws"), ((3000, 30), "f64", "auto")])
+@pytest.mark.parametrize("fraction", [0.25, 0.9])
+def test_minibatch_gd_matches_oracle(agd, ctx, oracle, shape, store, variant, fraction):
+    """GradientDescent.runMiniBatchSGD with miniBatchFraction < 1 on the same kernels (row mask +
+    selected-row count through the slabs), against the oracle's restatement with the same counter-based mask."""
+    n, d = shape
+    rng = np.random.default_rng(500 + n + d)
+    X, y = make_data(rng, n, d, "logistic", np.float32 if store == "f32" else np.float64)
+    w0 = rng.standard_normal(d) * 0.01
+    data = ctx.parallelize(y, X, store=store)
+    if variant != "auto":
+        data.set_option("k1_variant", variant)
+    w, hist = agd.GradientDescent.runMiniBatchSGD(data, agd.LogisticGradient(), agd.SquaredL2Updater(), 0.5, 12, 0.01,
+                                                  fraction, w0)
+    rw, rh = oracle.gd_run(oracle.Data(y, X=X), "logistic", "squared_l2", w0, step_size=0.5, num_iterations=12,
+                           reg_param=0.01, mini_batch_fraction=fraction)
+    assert len(hist) == len(rh) == 12
+    np.testing.assert_allclose(hist, rh, rtol=1e-11)
+    assert rel_err(w, rw) < 1e-10
+    full = agd.GradientDescent.runMiniBatchSGD(data, agd.LogisticGradient(), agd.SquaredL2Updater(), 0.5, 12, 0.01, 1.0, w0)
+    assert not np.allclose(full[1], hist)          # the mask really drops rows
+    data.close()
+
+
 def test_suite_T3_convergence_tol_on_gpu(agd, ctx, fixture_gd_input):             # Suite.scala:138-207
     y, X = fixture_gd_input
     data = ctx.parallelize(y, X).cache()
