@@ -113,6 +113,22 @@ int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype,
  * APPENDS `rows` rows: rowptr has rows+1 entries starting at 0 and is rebased onto the resident shard. */
 int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_t *idx, const void *val,
                  int32_t src_dtype, const double *labels, int64_t rows, int32_t d, int32_t store_dtype);
+/* LIBSVM text ingest (MLUtils.loadLibSVMFile of spark-mllib 1.3.0, the usual producer of the RDD handed to optimize):
+ * `label index:value ...` per line, one-based ascending indices, '#' comment lines and blank lines skipped,
+ * num_features <= 0 infers the dimension.  agd_libsvm_read parses on the host (no GPU needed) into an opaque
+ * object with accessors; agd_load_libsvm parses and appends the rows as CSR, split over the local GPUs. */
+typedef struct agd_libsvm agd_libsvm;
+int agd_libsvm_read(const char *path, int32_t num_features, agd_libsvm **out);
+int64_t agd_libsvm_rows(const agd_libsvm *L);
+int32_t agd_libsvm_dim(const agd_libsvm *L);
+int64_t agd_libsvm_nnz(const agd_libsvm *L);
+const int64_t *agd_libsvm_rowptr(const agd_libsvm *L);
+const int32_t *agd_libsvm_indices(const agd_libsvm *L);
+const double *agd_libsvm_values(const agd_libsvm *L);
+const double *agd_libsvm_labels(const agd_libsvm *L);
+const char *agd_libsvm_error(const agd_libsvm *L);
+void agd_libsvm_free(agd_libsvm *L);
+int agd_load_libsvm(agd_handle *h, const char *path, int32_t num_features, int32_t store_dtype);
 /* Drops every shard (all local devices). */
 int agd_clear(agd_handle *h);
 /* Rows currently resident on local device `dev`; feature count (0 when empty). */

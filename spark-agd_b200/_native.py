@@ -72,6 +72,17 @@ _SIGNATURES = {
                                  C.c_int32, C.c_int64, C.c_int32]),
     "agd_load_csr": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "agd_libsvm_read": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "agd_libsvm_rows": (C.c_int64, [C.c_void_p]),
+    "agd_libsvm_dim": (C.c_int32, [C.c_void_p]),
+    "agd_libsvm_nnz": (C.c_int64, [C.c_void_p]),
+    "agd_libsvm_rowptr": (C.c_void_p, [C.c_void_p]),
+    "agd_libsvm_indices": (C.c_void_p, [C.c_void_p]),
+    "agd_libsvm_values": (C.c_void_p, [C.c_void_p]),
+    "agd_libsvm_labels": (C.c_void_p, [C.c_void_p]),
+    "agd_libsvm_error": (C.c_char_p, [C.c_void_p]),
+    "agd_libsvm_free": (None, [C.c_void_p]),
+    "agd_load_libsvm": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]),
     "agd_clear": (C.c_int, [C.c_void_p]),
     "agd_rows": (C.c_int64, [C.c_void_p, C.c_int32]),
     "agd_dim": (C.c_int32, [C.c_void_p]),

@@ -283,6 +283,41 @@ class DeviceDataset:
             pass
 
 
+class MLUtils:
+    """org.apache.spark.mllib.util.MLUtils [mllib-1.3.0]: the ingest side of the path."""
+
+    @staticmethod
+    def parseLibSVMFile(path: str, numFeatures: int = -1):
+        """Host-only parse: (labels, rowptr, indices, values, d) with zero-based indices."""
+        L = N.lib()
+        obj = C.c_void_p()
+        rc = L.agd_libsvm_read(path.encode(), numFeatures, C.byref(obj))
+        try:
+            if rc != 0:
+                raise ValueError(L.agd_libsvm_error(obj).decode())
+            n, d, nnz = L.agd_libsvm_rows(obj), L.agd_libsvm_dim(obj), L.agd_libsvm_nnz(obj)
+
+            def arr(ptr, count, ctype, dtype):
+                if count == 0:
+                    return np.zeros(0, dtype=dtype)
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).astype(dtype, copy=True)
+
+            return (arr(L.agd_libsvm_labels(obj), n, C.c_double, np.float64),
+                    arr(L.agd_libsvm_rowptr(obj), n + 1, C.c_int64, np.int64),
+                    arr(L.agd_libsvm_indices(obj), nnz, C.c_int32, np.int32),
+                    arr(L.agd_libsvm_values(obj), nnz, C.c_double, np.float64), int(d))
+        finally:
+            L.agd_libsvm_free(obj)
+
+    @staticmethod
+    def loadLibSVMFile(sc: "Context", path: str, numFeatures: int = -1, store: str = "f64") -> "DeviceDataset":
+        """loadLibSVMFile(sc, path, numFeatures): rows land as CSR shards on the context's GPUs."""
+        ds = DeviceDataset(sc)
+        N.check(N.lib().agd_load_libsvm(ds.h, path.encode(), numFeatures, _STORE[store]), ds.h)
+        ds.total_rows = sum(ds.local_rows(i) for i in range(len(sc.devices)))
+        return ds
+
+
 @dataclass
 class RunStats:
     iterations: int
