@@ -44,6 +44,8 @@ def parse():
                          "ls_bf16 = configs[3] shape (--rows 50000000 --dim 4096); hinge_csr = configs[2] shape "
                          "(--rows 100000000 --dim 1000000 --nnz 64)")
     ap.add_argument("--nnz", type=int, default=64, help="stored entries per row for hinge_csr")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="all-reduce of the d+2 doubles: NVLink peer-memory exchange (default when mappable) or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = auto)")
@@ -206,6 +208,8 @@ def run_b200(args):
         data = ctx.synthetic_csr(total_rows, d, args.nnz, grad, seed=SEED, store=store)
     rows_local = data.local_rows(0)
     w0 = np.zeros(d)
+    if args.collective != "auto":
+        data.set_option("collective", args.collective)
     if wl != "logistic_f32":
         args.no_e2e = True
         args.no_cpu_baseline = True
@@ -284,7 +288,9 @@ def run_b200(args):
                          "note": "AGD_FLAG_MEMOIZE_FX: same weights and history bit for bit, fewer passes"},
             "allreduce_ms_per_pass": st.allreduce_ms_total / max(st.collective_calls, 1),
             "host_wall_s": st.seconds_total, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(st.gpu_launches), "collective_calls": int(st.collective_calls), "clocks": clocks,
+            "gpu_launches": int(st.gpu_launches), "collective_calls": int(st.collective_calls),
+            "collective": ("none" if world == 1 else ("nvlink peer-memory exchange" if st.collective_kind == 1 else "nccl all-reduce")),
+            "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     data.close()

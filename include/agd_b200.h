@@ -68,7 +68,7 @@ typedef struct {
   int32_t converged;      /* left through AGD.scala:319 or :323 */
   int32_t stopped_nan;    /* left through AGD.scala:309-312 */
   int32_t nonterminating; /* L became NaN: the reference would spin forever in :246-293; we stop */
-  int32_t reserved0;
+  int32_t collective_kind; /* 0 = none / NCCL all-reduce, 1 = one-shot exchange over NVLink peer memory */
   double final_L;
   double final_theta;
   double seconds_total;   /* host wall time inside agd_run */
@@ -177,7 +177,7 @@ int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, doubl
                          double reg_param, double mini_batch_fraction, const double *w0, double *w_out,
                          double *loss_hist, int32_t *n_hist, agd_stats *stats);
 
-/* Kernel-variant override for experiments/benchmarks: name in {"auto","ring","generic"}. */
+/* Options: "k1_variant" = auto|ring|generic|ws|tc, "collective" = auto|nccl|p2p, ring tuning knobs. */
 int agd_set_option(agd_handle *h, const char *key, const char *value);
 
 #ifdef __cplusplus

@@ -26,7 +26,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("passes", C.c_int32), ("backtracks", C.c_int32),
                 ("restarts", C.c_int32), ("converged", C.c_int32), ("stopped_nan", C.c_int32),
-                ("nonterminating", C.c_int32), ("reserved0", C.c_int32), ("final_L", C.c_double),
+                ("nonterminating", C.c_int32), ("collective_kind", C.c_int32), ("final_L", C.c_double),
                 ("final_theta", C.c_double), ("seconds_total", C.c_double), ("k1_ms_total", C.c_double),
                 ("k1_launches", C.c_int64), ("gpu_launches", C.c_int64), ("allreduce_ms_total", C.c_double),
                 ("device_ms_total", C.c_double), ("collective_calls", C.c_int64)]

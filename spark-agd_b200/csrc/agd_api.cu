@@ -28,6 +28,7 @@ struct NcclApi {
   decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
@@ -49,6 +50,7 @@ NcclApi &nccl_api() {
     AGD_NCCL_SYM(GetUniqueId)
     AGD_NCCL_SYM(CommInitRank)
     AGD_NCCL_SYM(AllReduce)
+    AGD_NCCL_SYM(AllGather)
     AGD_NCCL_SYM(GroupStart)
     AGD_NCCL_SYM(GroupEnd)
     AGD_NCCL_SYM(CommDestroy)
@@ -98,6 +100,12 @@ struct Dev {
   size_t ev_ar_used = 0;
   std::mutex *mu = nullptr;
   long long row_base = 0;          // global index of this shard's first row (for the sampling mask)
+  // K2' peer-memory exchange (xchg.cu)
+  double *xbuf = nullptr;                 // [2][W][d+2], written by every rank over NVLink
+  unsigned long long *xflags = nullptr;   // [2][W] epochs
+  unsigned int *xticket = nullptr;
+  XchgPeers xpeers;                       // every rank's xbuf / xflags as mapped into this device
+  std::vector<void *> xopened;            // cudaIpcOpenMemHandle mappings to close
 };
 
 }  // namespace
@@ -112,6 +120,10 @@ struct agd_handle {
   int tune_rows = 0, tune_ctas = 0;
   int k1_diag = 0;
   unsigned long long sample_seed = 0, sample_thresh = 0;  // mini-batch row mask of the current pass (0 = every row)
+  int collective = 0;        // 0 = auto (peer memory if every pair of ranks can map each other, else NCCL), 1 = nccl, 2 = p2p
+  int32_t x_d = 0;           // dimension the exchange buffers were built for (0 = not built)
+  bool x_p2p = false;        // exchange buffers are live
+  unsigned long long x_epoch = 0;
   std::string err;
   std::mutex mu;
   int64_t launches = 0;  // per device, current call
@@ -262,11 +274,153 @@ cudaEvent_t next_event(std::vector<cudaEvent_t> &pool, size_t &used) {
   return pool[used++];
 }
 
+
+void free_xchg(agd_handle *h) {
+  for (Dev &D : h->devs) {
+    cudaSetDevice(D.ordinal);
+    for (void *p : D.xopened) cudaIpcCloseMemHandle(p);
+    D.xopened.clear();
+    if (D.xbuf) cudaFree(D.xbuf);
+    if (D.xflags) cudaFree(D.xflags);
+    if (D.xticket) cudaFree(D.xticket);
+    D.xbuf = nullptr; D.xflags = nullptr; D.xticket = nullptr;
+  }
+  h->x_d = 0;
+  h->x_p2p = false;
+}
+
+// Builds the peer-memory exchange for the current dimension: every rank allocates xbuf/xflags, the CUDA IPC handles
+// travel once through an NCCL all-gather (setup only), remote ranks are mapped with cudaIpcOpenMemHandle and local
+// devices of this process with peer access.  Collective: every rank calls it from the same entry point.
+int ensure_xchg(agd_handle *h) {
+  if (h->world <= 1 || h->collective == 1) return 0;
+  if (h->x_d == h->d) return 0;
+  free_xchg(h);
+  h->x_d = h->d;
+  const int W = h->world, nd = (int)h->devs.size();
+  if (W > kMaxRanks) { if (h->collective == 2) return fail(h, "peer exchange supports at most %d ranks", kMaxRanks); return 0; }
+  NcclApi &N = nccl_api();
+  const size_t n = (size_t)h->d + 2;
+  struct Handles { cudaIpcMemHandle_t buf, flags; int can_peer; int pad[3]; };
+  std::vector<Handles> mine(nd), all((size_t)W);
+  // 1. allocate + export
+  for (int i = 0; i < nd; ++i) {
+    Dev &D = h->devs[i];
+    CK(cudaSetDevice(D.ordinal));
+    CK(cudaMalloc(&D.xbuf, 2 * (size_t)W * n * sizeof(double)));
+    CK(cudaMalloc(&D.xflags, 2 * (size_t)W * sizeof(unsigned long long)));
+    CK(cudaMalloc(&D.xticket, sizeof(unsigned int)));
+    CK(cudaMemset(D.xbuf, 0, 2 * (size_t)W * n * sizeof(double)));
+    CK(cudaMemset(D.xflags, 0, 2 * (size_t)W * sizeof(unsigned long long)));
+    CK(cudaMemset(D.xticket, 0, sizeof(unsigned int)));
+    memset(&mine[i], 0, sizeof(Handles));
+    mine[i].can_peer = 1;
+    for (int j = 0; j < nd; ++j) {
+      if (j == i) continue;
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, D.ordinal, h->devs[j].ordinal));
+      if (!can) mine[i].can_peer = 0;
+      else { cudaError_t e = cudaDeviceEnablePeerAccess(h->devs[j].ordinal, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) mine[i].can_peer = 0; cudaGetLastError(); }
+    }
+    if (cudaIpcGetMemHandle(&mine[i].buf, D.xbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine[i].flags, D.xflags) != cudaSuccess) {
+      mine[i].can_peer = 0;
+      cudaGetLastError();
+    }
+  }
+  // 2. all-gather the handles (device staging through NCCL; setup only)
+  {
+    std::vector<void *> stage(nd);
+    for (int i = 0; i < nd; ++i) {
+      Dev &D = h->devs[i];
+      CK(cudaSetDevice(D.ordinal));
+      CK(cudaMalloc(&stage[i], (size_t)W * sizeof(Handles)));
+      CK(cudaMemcpyAsync((char *)stage[i] + (size_t)(h->first_rank + i) * sizeof(Handles), &mine[i], sizeof(Handles), cudaMemcpyHostToDevice, D.st));
+    }
+    CKN(N.GroupStart());
+    for (int i = 0; i < nd; ++i) {
+      Dev &D = h->devs[i];
+      CKN(N.AllGather((char *)stage[i] + (size_t)(h->first_rank + i) * sizeof(Handles), stage[i], sizeof(Handles), ncclChar, D.comm, D.st));
+    }
+    CKN(N.GroupEnd());
+    CK(cudaSetDevice(h->devs[0].ordinal));
+    CK(cudaMemcpyAsync(all.data(), stage[0], (size_t)W * sizeof(Handles), cudaMemcpyDeviceToHost, h->devs[0].st));
+    for (int i = 0; i < nd; ++i) { CK(cudaSetDevice(h->devs[i].ordinal)); CK(cudaStreamSynchronize(h->devs[i].st)); }
+    for (int i = 0; i < nd; ++i) { cudaSetDevice(h->devs[i].ordinal); cudaFree(stage[i]); }
+  }
+  bool ok = true;
+  for (int r = 0; r < W; ++r) ok = ok && all[r].can_peer;
+  // 3. map every rank's buffers into every local device
+  for (int i = 0; i < nd && ok; ++i) {
+    Dev &D = h->devs[i];
+    CK(cudaSetDevice(D.ordinal));
+    for (int r = 0; r < W; ++r) {
+      const int lj = r - h->first_rank;
+      if (lj >= 0 && lj < nd) {  // same process: direct pointers (peer access enabled above)
+        D.xpeers.slot[r] = h->devs[lj].xbuf;
+        D.xpeers.flag[r] = h->devs[lj].xflags;
+        continue;
+      }
+      void *pb = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pb, all[r].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        break;
+      }
+      D.xopened.push_back(pb);
+      D.xopened.push_back(pf);
+      D.xpeers.slot[r] = (double *)pb;
+      D.xpeers.flag[r] = (unsigned long long *)pf;
+    }
+  }
+  // every rank must take the same decision: agree through one more (tiny) all-reduce of the ok flag
+  {
+    int *flagdev = nullptr;
+    Dev &D0 = h->devs[0];
+    CK(cudaSetDevice(D0.ordinal));
+    CK(cudaMalloc(&flagdev, sizeof(int) * nd));
+    int v = ok ? 1 : 0;
+    std::vector<int *> fl(nd);
+    for (int i = 0; i < nd; ++i) {
+      CK(cudaSetDevice(h->devs[i].ordinal));
+      CK(cudaMalloc(&fl[i], sizeof(int)));
+      CK(cudaMemcpyAsync(fl[i], &v, sizeof(int), cudaMemcpyHostToDevice, h->devs[i].st));
+    }
+    CKN(N.GroupStart());
+    for (int i = 0; i < nd; ++i) CKN(N.AllReduce(fl[i], fl[i], 1, ncclInt, ncclMin, h->devs[i].comm, h->devs[i].st));
+    CKN(N.GroupEnd());
+    CK(cudaSetDevice(D0.ordinal));
+    CK(cudaMemcpyAsync(&v, fl[0], sizeof(int), cudaMemcpyDeviceToHost, D0.st));
+    for (int i = 0; i < nd; ++i) { CK(cudaSetDevice(h->devs[i].ordinal)); CK(cudaStreamSynchronize(h->devs[i].st)); cudaFree(fl[i]); }
+    cudaSetDevice(D0.ordinal);
+    cudaFree(flagdev);
+    ok = v == 1;
+  }
+  if (!ok) {
+    if (h->collective == 2) return fail(h, "peer-memory exchange unavailable (no P2P / IPC mapping between every pair of ranks)");
+    const int32_t keep = h->x_d;
+    free_xchg(h);
+    h->x_d = keep;  // do not retry every pass; NCCL carries the all-reduce
+    return 0;
+  }
+  h->x_p2p = true;
+  h->x_epoch = 0;
+  return 0;
+}
+
 // One applySmooth (AGD.scala:192-208) at the device-resident point `w_of(dev)`: K1 over every local
 // shard, slab reduction, one all-reduce of [grad | loss | count].  Result: Dev::acc on every device.
 template <typename WSel>
 int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
   const int32_t d = h->d;
+  const bool p2p = h->world > 1 && h->x_p2p;
+  const unsigned long long epoch = p2p ? ++h->x_epoch : 0ull;
+  auto make_pub = [&](Dev &D, size_t i) {
+    XchgPub pub;
+    pub.peers = D.xpeers; pub.world = h->world; pub.my_rank = h->first_rank + (int)i; pub.buf = (int)(epoch & 1ull);
+    pub.n = d + 2; pub.epoch = epoch; pub.ticket = D.xticket;
+    return pub;
+  };
   for (size_t i = 0; i < h->devs.size(); ++i) {
     Dev &D = h->devs[i];
     CK(cudaSetDevice(D.ordinal));
@@ -280,7 +434,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
       CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-      h->launches += (i == 0) ? 2 : 0;
+      if (p2p) { const XchgPub pub = make_pub(D, i); CK(xchg_publish_launch(D.acc, pub, D.st)); }
+      h->launches += (i == 0) ? (p2p ? 3 : 2) : 0;
       continue;
     }
     K1Args a;
@@ -308,10 +463,21 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     else if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
     else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-    CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, D.st));
+    if (p2p) { const XchgPub pub = make_pub(D, i); CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, &pub, D.st)); }
+    else CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, nullptr, D.st));
     if (i == 0) h->launches += (s.rows > 0 ? 2 : 1);
   }
-  if (h->world > 1) {
+  if (p2p) {  // K2': every rank already holds every rank's partial sums; add them in rank order
+    Dev &D0 = h->devs[0];
+    if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
+    for (Dev &D : h->devs) {
+      CK(cudaSetDevice(D.ordinal));
+      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), d + 2, epoch, D.acc, D.st));
+    }
+    if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
+    h->launches += 1;
+    h->collectives += 1;
+  } else if (h->world > 1) {
     if (!h->comm_ready) return fail(h, "world_ranks=%d but agd_comm_init was not called", h->world);
     NcclApi &N = nccl_api();
     Dev &D0 = h->devs[0];
@@ -349,7 +515,8 @@ int check_ready(agd_handle *h) {
   if (h->d <= 0) return fail(h, "no shard loaded (call agd_load_dense / agd_load_csr / agd_generate first)");
   for (Dev &D : h->devs)
     if (ensure_vectors(h, D, h->d)) return 1;
-  return 0;
+  if (h->world > 1 && !h->comm_ready) return fail(h, "world_ranks=%d but agd_comm_init was not called", h->world);
+  return ensure_xchg(h);
 }
 
 int call_begin(agd_handle *h) {
@@ -377,6 +544,7 @@ int call_end(agd_handle *h, agd_stats &s, std::chrono::steady_clock::time_point 
   s.k1_launches = (int64_t)(D0.ev_used / 2);
   s.gpu_launches = h->launches;
   s.collective_calls = h->collectives;
+  s.collective_kind = h->x_p2p ? 1 : 0;
   s.seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   return 0;
 }
@@ -471,6 +639,7 @@ int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
 
 int agd_destroy(agd_handle *h) {
   if (!h) return 0;
+  free_xchg(h);
   for (Dev &D : h->devs) {
     cudaSetDevice(D.ordinal);
     cudaStreamSynchronize(D.st);
@@ -798,6 +967,14 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
     return 0;
   }
   if (!strcmp(key, "ring_stages")) { h->ring_stages = atoi(value); return 0; }
+  if (!strcmp(key, "collective")) {
+    if (!strcmp(value, "auto")) h->collective = 0;
+    else if (!strcmp(value, "nccl")) h->collective = 1;
+    else if (!strcmp(value, "p2p")) h->collective = 2;
+    else return fail(h, "collective must be auto|nccl|p2p");
+    free_xchg(h);
+    return 0;
+  }
   if (!strcmp(key, "k1_diag")) { h->k1_diag = atoi(value); return 0; }
   if (!strcmp(key, "ring_rows")) { h->tune_rows = atoi(value); return 0; }
   if (!strcmp(key, "ring_ctas")) { h->tune_ctas = atoi(value); return 0; }

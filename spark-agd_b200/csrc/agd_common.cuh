@@ -35,8 +35,31 @@ int k1_max_blocks(int sm_count);
 // bf16 shards: margins on CUDA cores, X^T r on tcgen05 (k1_tc.cu); d % 128 == 0, d <= 4096
 int k1_tc_supported(int32_t d, int elem_bytes);
 cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStream_t st);
-// out[c] = sum_b slabs[b][c] for c <= d + 1 (gradient sums, loss sum, row count; fixed order => deterministic)
-cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st);
+// ---------------------------------------------------------------- K2': one-shot all-reduce over NVLink peer memory
+// Every rank owns an exchange buffer xbuf[2][W][n] (+ flags[2][W]) that all peers can store into (P2P / CUDA IPC).
+// publish: rank r stores its n = d+2 partial sums into slot r of EVERY rank's buffer, fences, then raises the flag
+// (epoch) -- fused into the tail of k1_reduce_kernel, or standalone for the CSR path.  gather: each rank waits for the
+// W flags of the epoch and adds the W slots in rank order, so every rank gets the same bits (replaces combOp +
+// treeAggregate + broadcast, AGD.scala:193-204, without a library call in the loop).  Buffers alternate by epoch parity.
+constexpr int kMaxRanks = 16;
+struct XchgPeers {
+  double *slot[kMaxRanks];               // base of rank p's xbuf as mapped into THIS device
+  unsigned long long *flag[kMaxRanks];   // base of rank p's flags
+};
+struct XchgPub {
+  XchgPeers peers;
+  int world, my_rank, buf, n;
+  unsigned long long epoch;
+  unsigned int *ticket;
+};
+cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStream_t st);
+cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
+                               unsigned long long epoch, double *acc_out, cudaStream_t st);
+
+// out[c] = sum_b slabs[b][c] for c <= d + 1 (gradient sums, loss sum, row count; fixed order => deterministic);
+// with pub != nullptr the sums are also stored into every peer's exchange slot and the epoch flag is raised
+cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, const XchgPub *pub,
+                             cudaStream_t st);
 
 // CSR variant (k1_csr.cu)
 struct K1CsrArgs {

@@ -660,9 +660,11 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
 // out[c] = sum over slabs of column c, c <= d + 1 (gradient, loss sum, row count).  32 columns per block; 8 slab groups per block sum
 // strided subsets (slab b -> group b % 8) with 4 loads in flight, then group 0 adds the 8 group sums in
 // order: the summation tree is fixed, so the result is bit-reproducible.
+template <bool PUB>
 __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int d,
-                                                        long long rows, double *__restrict__ out) {
+                                                        double *__restrict__ out, const XchgPub pub) {
   __shared__ double part[8][33];
+  __shared__ bool last;
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const size_t stride = (size_t)d + 2;
@@ -683,8 +685,23 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
 #pragma unroll
     for (int gi = 0; gi < 8; ++gi) t += part[gi][cl];
     out[c] = t;
+    if (PUB) {  // compute + collective in one kernel: the result goes straight into every peer's HBM over NVLink
+      const size_t off = ((size_t)pub.buf * pub.world + pub.my_rank) * pub.n + c;
+      for (int p = 0; p < pub.world; ++p) pub.peers.slot[p][off] = t;
+    }
   }
-  (void)rows;
+  if (PUB) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(pub.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+      __threadfence_system();
+      if (threadIdx.x < pub.world)
+        *reinterpret_cast<volatile unsigned long long *>(&pub.peers.flag[threadIdx.x][pub.buf * pub.world + pub.my_rank]) = pub.epoch;
+      if (threadIdx.x == 0) *pub.ticket = 0u;
+    }
+  }
 }
 
 struct RingShape { int tpr, v, r; };
@@ -871,9 +888,12 @@ cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int
   return cudaGetLastError();
 }
 
-cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, cudaStream_t st) {
+cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, const XchgPub *pub,
+                             cudaStream_t st) {
+  (void)rows;
   const int grid = (d + 2 + 31) / 32;
-  k1_reduce_kernel<<<grid, 256, 0, st>>>(slabs, blocks, d, (long long)rows, out);
+  if (pub) k1_reduce_kernel<true><<<grid, 256, 0, st>>>(slabs, blocks, d, out, *pub);
+  else k1_reduce_kernel<false><<<grid, 256, 0, st>>>(slabs, blocks, d, out, XchgPub());
   return cudaGetLastError();
 }
 

@@ -336,12 +336,13 @@ class RunStats:
     allreduce_ms_total: float
     device_ms_total: float
     collective_calls: int
+    collective_kind: int = 0
 
 
 def _stats(st: N.Stats) -> RunStats:
     return RunStats(st.iterations, st.passes, st.backtracks, st.restarts, bool(st.converged), bool(st.stopped_nan),
                     bool(st.nonterminating), st.final_L, st.final_theta, st.seconds_total, st.k1_ms_total,
-                    st.k1_launches, st.gpu_launches, st.allreduce_ms_total, st.device_ms_total, st.collective_calls)
+                    st.k1_launches, st.gpu_launches, st.allreduce_ms_total, st.device_ms_total, st.collective_calls, st.collective_kind)
 
 
 # --------------------------------------------------------------------------- the optimizer

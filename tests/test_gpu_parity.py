@@ -546,7 +546,8 @@ def test_full_size_properties(agd, ctx, oracle):
 
 
 # ------------------------------------------------------------------ several GPUs in one process
-def test_two_local_gpus_match_one(agd, oracle):
+@pytest.mark.parametrize("collective", ["p2p", "nccl"])
+def test_two_local_gpus_match_one(agd, oracle, collective):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -554,7 +555,9 @@ def test_two_local_gpus_match_one(agd, oracle):
     X, y = make_data(rng, 30001, 1024, "logistic", np.float32)
     w0 = np.zeros(1024)
     two = agd.Context(devices=[0, 1]).parallelize(y, X, store="f32")
+    two.set_option("collective", collective)
     w, hist, st = agd.run_with_stats(two, agd.LogisticGradient(), agd.SquaredL2Updater(), 0.0, 8, 0.01, w0)
+    assert st.collective_kind == (1 if collective == "p2p" else 0) and st.collective_calls == st.passes
     ref = oracle.agd_run(oracle.Data(y, X=X), "logistic", "squared_l2", w0, convergence_tol=0.0, num_iterations=8,
                          reg_param=0.01)
     np.testing.assert_allclose(hist, ref.loss_history, rtol=1e-11)
