@@ -77,7 +77,9 @@ typedef struct {
   int64_t gpu_launches;   /* this library's own kernel launches issued by the call, per device */
   double allreduce_ms_total; /* CUDA-event time of the all-reduce (0 when world == 1) */
   double device_ms_total;    /* CUDA events on device 0's stream around the whole call */
-  int64_t collective_calls;  /* all-reduces enqueued per device (library kernels, not counted in gpu_launches) */
+  int64_t collective_calls;  /* all-reduces enqueued per device */
+  int32_t wasted_passes;     /* speculative applySmooth(x) passes discarded because ||x-y||^2 == 0 (AGD.scala:265) */
+  int32_t reserved1;
 } agd_stats;
 
 /* ---- lifecycle ---- */

@@ -29,7 +29,8 @@ class Stats(C.Structure):
                 ("nonterminating", C.c_int32), ("collective_kind", C.c_int32), ("final_L", C.c_double),
                 ("final_theta", C.c_double), ("seconds_total", C.c_double), ("k1_ms_total", C.c_double),
                 ("k1_launches", C.c_int64), ("gpu_launches", C.c_int64), ("allreduce_ms_total", C.c_double),
-                ("device_ms_total", C.c_double), ("collective_calls", C.c_int64)]
+                ("device_ms_total", C.c_double), ("collective_calls", C.c_int64), ("wasted_passes", C.c_int32),
+                ("reserved1", C.c_int32)]
 
 
 def _sources():

@@ -100,6 +100,8 @@ struct Dev {
   size_t ev_ar_used = 0;
   std::mutex *mu = nullptr;
   long long row_base = 0;          // global index of this shard's first row (for the sampling mask)
+  double *hist_host = nullptr;            // pinned: [2k] = loss sum, [2k+1] = count of the history pass of iteration k
+  size_t hist_cap = 0;
   // K2' peer-memory exchange (xchg.cu)
   double *xbuf = nullptr;                 // [2][W][d+2], written by every rank over NVLink
   unsigned long long *xflags = nullptr;   // [2][W] epochs
@@ -650,6 +652,7 @@ int agd_destroy(agd_handle *h) {
       if (p) cudaFree(p);
     if (D.ticket) cudaFree(D.ticket);
     if (D.scalars_host) cudaFreeHost(D.scalars_host);
+    if (D.hist_host) cudaFreeHost(D.hist_host);
     if (D.stage_dev) cudaFree(D.stage_dev);
     for (cudaEvent_t e : D.ev) cudaEventDestroy(e);
     for (cudaEvent_t e : D.ev_ar) cudaEventDestroy(e);
@@ -1071,6 +1074,19 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     return 0;
   };
 
+  // Host round trips: the host needs device scalars once per backtracking round.  Pass 2 (applySmooth(x), :269) is
+  // enqueued speculatively right behind pass 1 -- it is wasted only when ||x - y||^2 == 0 (:265) -- and the f_x of the
+  // history pass (:304) is copied to pinned memory asynchronously and read after the loop, so the GPU runs
+  // pass 3(k) -> pass 1(k+1) -> pass 2(k+1) back to back with a single synchronisation per round.
+  Dev &H0 = h->devs[0];
+  if (H0.hist_cap < 2 * (size_t)(p->num_iterations > 0 ? p->num_iterations : 1)) {
+    CK(cudaSetDevice(H0.ordinal));
+    if (H0.hist_host) cudaFreeHost(H0.hist_host);
+    H0.hist_cap = 2 * (size_t)(p->num_iterations > 0 ? p->num_iterations : 1);
+    CK(cudaHostAlloc(&H0.hist_host, H0.hist_cap * sizeof(double), cudaHostAllocDefault));
+  }
+  std::vector<double> cx_of;          // c_x per iteration (:305)
+  std::vector<char> fx_deferred;      // f_x of iteration k still sits in H0.hist_host[2k..2k+1]
   for (int nIter = 1; nIter <= p->num_iterations; ++nIter) {              // :237
     const double L_old = L;                                                // :242
     L = L * p->alpha;                                                      // :243
@@ -1094,27 +1110,25 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
             a.theta = theta; a.one_minus_theta = omt; a.step = step; a.reg = p->reg_param; a.d = d; a.updater = p->updater;
             return k3_step_launch(a, D.st);
           })) return 1;
-      if (read_scalars(h, sc)) return 1;
+      const bool speculate = beta < 1.0;                                   // :257 is known up front
+      if (speculate) {                                                     // :269, enqueued before :265 is known
+        if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
+        if (launch_all([&](Dev &D) {
+              K3GxArgs a;
+              a.acc = D.acc; a.x = D.x; a.y = D.y; a.g_y = D.g_y; a.g_x = D.g_x; a.partials = D.partials;
+              a.ticket = D.ticket; a.scalars = D.scalars_dev + K3_NS; a.d = d;
+              return k3_gx_launch(a, D.st);
+            })) return 1;
+      }
+      if (read_scalars(h, sc)) return 1;                                   // the one synchronisation of this round
+      memcpy(sg, H0.scalars_host + K3_NS, K3_NS * sizeof(double));
       f_y = sc[6] / sc[7];                                                 // :207
       have_fx = false;
       if (beta >= 1.0) break;                                              // :257
       const double nxy = std::sqrt(sc[0]);
       const double xy_sq = nxy * nxy;                                      // :264  math.pow(norm(xy), 2)
-      if (xy_sq == 0) break;                                               // :265
-      if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;  // :269
+      if (xy_sq == 0) { s.wasted_passes++; break; }                        // :265  (the speculative pass is discarded)
       s.passes++;
-      if (launch_all([&](Dev &D) {
-            K3GxArgs a;
-            a.acc = D.acc; a.x = D.x; a.y = D.y; a.g_y = D.g_y; a.g_x = D.g_x; a.partials = D.partials;
-            a.ticket = D.ticket; a.scalars = D.scalars_dev + K3_NS; a.d = d;
-            return k3_gx_launch(a, D.st);
-          })) return 1;
-      {
-        Dev &D = h->devs[0];
-        CK(cudaSetDevice(D.ordinal));
-        CK(cudaStreamSynchronize(D.st));
-        memcpy(sg, D.scalars_host + K3_NS, K3_NS * sizeof(double));
-      }
       f_x = sg[6] / sg[7];
       have_fx = true;
       double localL;
@@ -1132,20 +1146,19 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       s.backtracks++;
       if (L != L) { nonterminating = true; break; }  // the reference never leaves :246-293 once L is NaN
     }
+    const double c_x = reg_value(p->updater, p->reg_param, sc[2], sc[5]);  // :305  applyProjector(x, g_x, 0.0)._1
+    cx_of.push_back(c_x);
     if (!(memoize && have_fx)) {                                           // :304  (f_x, g_x) = applySmooth(x)
       if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
       s.passes++;
-      {
-        Dev &D = h->devs[0];
-        CK(cudaSetDevice(D.ordinal));
-        double tail[2];
-        CK(cudaMemcpyAsync(tail, D.acc + d, 2 * sizeof(double), cudaMemcpyDeviceToHost, D.st));
-        CK(cudaStreamSynchronize(D.st));
-        f_x = tail[0] / tail[1];
-      }
+      CK(cudaSetDevice(H0.ordinal));
+      CK(cudaMemcpyAsync(H0.hist_host + 2 * (size_t)nh, H0.acc + d, 2 * sizeof(double), cudaMemcpyDeviceToHost, H0.st));
+      fx_deferred.push_back(1);                                            // read after the loop
+      loss_hist[nh++] = 0.0;
+    } else {
+      fx_deferred.push_back(0);
+      loss_hist[nh++] = f_x + c_x;                                         // :306
     }
-    const double c_x = reg_value(p->updater, p->reg_param, sc[2], sc[5]);  // :305  applyProjector(x, g_x, 0.0)._1
-    loss_hist[nh++] = f_x + c_x;                                           // :306
     s.iterations = nIter;
     if (nonterminating) { s.stopped_nan = 1; s.nonterminating = 1; break; }
     if (std::isnan(f_y) || std::isinf(f_y)) { s.stopped_nan = 1; break; }  // :309-312
@@ -1166,6 +1179,8 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));    // :337
   }
   if (call_end(h, s, t_begin)) return 1;
+  for (int k = 0; k < nh; ++k)                                             // :306 for the deferred f_x values
+    if (fx_deferred[(size_t)k]) loss_hist[k] = H0.hist_host[2 * (size_t)k] / H0.hist_host[2 * (size_t)k + 1] + cx_of[(size_t)k];
   *n_hist = nh;
   s.final_L = L;
   s.final_theta = theta;

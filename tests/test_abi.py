@@ -33,7 +33,7 @@ def test_struct_layouts_match_header(agd):
         (1e-4, 100, 0.0, 1.0, 0.5, 0.9, 1)          # AGD.scala:44-51
     assert p.Lexact == float("inf") and p.flags == 0
     assert ctypes.sizeof(N.Params) == N.lib().agd_sizeof_params() == 72
-    assert ctypes.sizeof(N.Stats) == N.lib().agd_sizeof_stats() == 104
+    assert ctypes.sizeof(N.Stats) == N.lib().agd_sizeof_stats() == 112
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
