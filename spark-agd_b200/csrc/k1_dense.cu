@@ -258,33 +258,49 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     if ((lane % (32 / R)) == 0) partial[(g * R + lane / (32 / R)) * 8 + wig] = tot;
     __syncthreads();
 
+    // scalar section: only the multiplier is needed by phase 2, so for logistic only the exp + reciprocal part of
+    // the evaluation sits between the barriers; the log part follows, interleaved with this warp's phase-2 FMAs
+    LogisticMid mid = {0.0, 0.0, 1.0, 1.0};
+    bool row_ok = false;
     if (warp == sw && lane < TR) {
       double pw[8];
 #pragma unroll
       for (int wi = 0; wi < 8; ++wi) pw[wi] = (wi < WPG) ? partial[lane * 8 + wi] : 0.0;
       const double m = ((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7]));
-      double mult, loss;
-      loss_eval(a.kind, m, ylab, mult, loss);
-      const bool valid = lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + lane);
-      mult_s[lane] = valid ? mult : 0.0;
-      lossacc += valid ? loss : 0.0;
-      cntacc += valid ? 1.0 : 0.0;
+      row_ok = lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + lane);
+      double mult, loss = 0.0;
+      if (a.kind == AGD_GRAD_LOGISTIC) mult = logistic_head(m, ylab, mid);
+      else loss_eval(a.kind, m, ylab, mult, loss);
+      mult_s[lane] = row_ok ? mult : 0.0;
+      if (a.kind != AGD_GRAD_LOGISTIC) lossacc += row_ok ? loss : 0.0;
+      cntacc += row_ok ? 1.0 : 0.0;
     }
     __syncthreads();
 
-    // phase 2: g += mult_i * x_i on the retained fp64 tile
-    double mu[R];
+    // phase 2: g += mult_i * x_i on the retained fp64 tile (two accumulator sets: dependency chains of R/2)
+    auto phase2 = [&]() {
+      double mu[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) mu[r] = mult_s[g * R + r];
+      for (int r = 0; r < R; ++r) mu[r] = mult_s[g * R + r];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+      for (int r = 0; r < R; ++r) {
 #pragma unroll
-      for (int v = 0; v < V; ++v)
+        for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-          if (R > 1 && (r & 1)) acc2[v][e] = fma(mu[r], xd[r][v][e], acc2[v][e]);
-          else acc[v][e] = fma(mu[r], xd[r][v][e], acc[v][e]);
-        }
+          for (int e = 0; e < EPV; ++e) {
+            if (R > 1 && (r & 1)) acc2[v][e] = fma(mu[r], xd[r][v][e], acc2[v][e]);
+            else acc[v][e] = fma(mu[r], xd[r][v][e], acc[v][e]);
+          }
+      }
+    };
+    if (a.kind == AGD_GRAD_LOGISTIC && warp == sw) {
+      // warp-uniform branch: the log chain of the loss (all 32 lanes, lanes >= TR carry don't-care values) is
+      // independent of the FMAs, so the scheduler interleaves the two instead of serialising them
+      const double loss = logistic_tail(mid, ylab);
+      phase2();
+      lossacc += row_ok ? loss : 0.0;
+    } else {
+      phase2();
     }
   }
 #pragma unroll

@@ -37,8 +37,12 @@ __device__ __forceinline__ double rcp_1to4(double u) {  // u in [1, 4)
   return fma(y, e, y);
 }
 
-// mult = 1/(1+exp(margin)) - y ; loss = y > 0 ? log1pExp(margin) : log1pExp(margin) - margin, margin = -m
-__device__ __forceinline__ void logistic_eval(double m, double y, double &mult, double &loss) {
+// The evaluation is split so that a kernel can put only what phase 2 needs (the multiplier) between its barriers:
+//   logistic_head: e = exp(-|margin|), u = 1 + e, q = 1/u  ->  mult = sigmoid - y        (exp chain + reciprocal)
+//   logistic_tail: log1p(e) = log(u) + (e - (u - 1)) * q   ->  loss                      (log chain, off the critical path)
+struct LogisticMid { double margin, e, u, q; };
+
+__device__ __forceinline__ double logistic_head(double m, double y, LogisticMid &mid) {
   const double margin = -1.0 * m;
   const double a = fabs(m);
   // e = exp(-a): -a = (32*me + j) * ln2/32 + r
@@ -59,9 +63,15 @@ __device__ __forceinline__ void logistic_eval(double m, double y, double &mult, 
   if (a > 700.0) e = 0.0;
   if (a != a) e = a;  // NaN margin propagates, as it does through Math.exp
   const double u = 1.0 + e;
-  const double c = e - (u - 1.0);
-  // q = 1/u  ||  log(u), u in [1,2]
   const double q = rcp_1to4(u);
+  mid.margin = margin; mid.e = e; mid.u = u; mid.q = q;
+  const double sig = (margin > 0) ? e * q : q;
+  return sig - y;
+}
+
+__device__ __forceinline__ double logistic_tail(const LogisticMid &mid, double y) {
+  const double e = mid.e, u = mid.u, q = mid.q, margin = mid.margin;
+  const double c = e - (u - 1.0);
   const bool big = u > 1.4142135623730951;
   const double f = (big ? u * 0.5 : u) - 1.0;
   const double d2 = 2.0 + f;
@@ -77,10 +87,15 @@ __device__ __forceinline__ void logistic_eval(double m, double y, double &mult, 
   const double kf = big ? 1.0 : 0.0;
   const double logu = kf * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + kf * 1.90821492927058770002e-10)) - f);
   const double L = fma(c, q, logu);  // log1p(e)
-  const double sig = (margin > 0) ? e * q : q;
-  mult = sig - y;
   const double l1 = (margin > 0) ? margin + L : L;
-  loss = (y > 0) ? l1 : l1 - margin;
+  return (y > 0) ? l1 : l1 - margin;
+}
+
+// mult = 1/(1+exp(margin)) - y ; loss = y > 0 ? log1pExp(margin) : log1pExp(margin) - margin, margin = -m
+__device__ __forceinline__ void logistic_eval(double m, double y, double &mult, double &loss) {
+  LogisticMid mid;
+  mult = logistic_head(m, y, mid);
+  loss = logistic_tail(mid, y);
 }
 
 // loss'(margin) and loss for one example; `m` = x.w.  Formulas: Gradient.scala of spark-mllib 1.3.0.

@@ -16,10 +16,7 @@ def t(label, grad=S.LogisticGradient(), **opts):
     ms = st.k1_ms_total / st.k1_launches
     print(json.dumps(dict(label=label, **opts, k1_ms=round(ms, 3), gbs=round(bytes_pass / ms / 1e6, 1),
                           frac=round(bytes_pass / ms / 1e6 / 6566.1, 4))), flush=True)
-for rep in range(2):
-    t("ring logistic", k1_variant="ring", ring_bcast=0)
+for rep in range(3):
+    t("ring logistic", k1_variant="ring")
     t("ring LS", grad=S.LeastSquaresGradient())
     t("ring hinge", grad=S.HingeGradient())
-    t("ring logistic bcast", ring_bcast=1)
-    t("ring LS bcast", grad=S.LeastSquaresGradient())
-t("101 stream+phase1", k1_diag=101, ring_bcast=0)
