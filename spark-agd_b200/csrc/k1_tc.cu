@@ -294,6 +294,17 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
     const int rq = tid >> 6;        // rows rq and rq + 8
     const int vv = tid & 63;        // 16-byte vector within the group row
     mbar_wait(wbar, 0);
+    // one-time re-layout of w: within each 64-byte chunk c (8 features) swap the four 16-byte pairs j -> j ^ ((c>>1)&3)
+    for (int c = tid; c < a.d / 8; c += kConsumers) {
+      const int f = (c >> 1) & 3;
+      if (f) {
+        double2 *blk = reinterpret_cast<double2 *>(w_s + (size_t)c * 8);
+        const double2 t0 = blk[0], t1 = blk[1], t2 = blk[2], t3 = blk[3];
+        const double2 v[4] = {t0, t1, t2, t3};
+        blk[0 ^ f] = v[0]; blk[1 ^ f] = v[1]; blk[2 ^ f] = v[2]; blk[3 ^ f] = v[3];
+      }
+    }
+    named_sync(5, kConsumers);
     int slot = -1;
     uint32_t par = 1;               // ring slot and its mbarrier phase, kept incrementally
     const int blk = vv >> 3, ch = vv & 7;
@@ -313,21 +324,12 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
           const unsigned char *gbase = smem + (uint32_t)slot * (uint32_t)group_bytes;
           const uint4 r0 = *reinterpret_cast<const uint4 *>(gbase + x_off0);
           const uint4 r1 = *reinterpret_cast<const uint4 *>(gbase + x_off1);
-          // w pairs are read in a lane-rotated order (unit j = i ^ sw) so that the 8 lanes of a quarter-warp
-          // touch 8 different 16-byte bank groups (a plain 64-byte lane stride is a 4-way conflict); the x
-          // words are rotated the same way -- a dot product does not care about the order of its terms
-          uint32_t w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
-          if (sw & 1) {
-            uint32_t t0 = w0[0]; w0[0] = w0[1]; w0[1] = t0; t0 = w0[2]; w0[2] = w0[3]; w0[3] = t0;
-            uint32_t t1 = w1[0]; w1[0] = w1[1]; w1[1] = t1; t1 = w1[2]; w1[2] = w1[3]; w1[3] = t1;
-          }
-          if (sw & 2) {
-            uint32_t t0 = w0[0]; w0[0] = w0[2]; w0[2] = t0; t0 = w0[1]; w0[1] = w0[3]; w0[3] = t0;
-            uint32_t t1 = w1[0]; w1[0] = w1[2]; w1[2] = t1; t1 = w1[1]; w1[1] = w1[3]; w1[3] = t1;
-          }
+          // w was re-laid out once per CTA (below): the 16-byte pair j of chunk c sits at position j ^ ((c >> 1) & 3), so
+          // the 8 lanes of a quarter-warp touch 8 different bank groups with no per-element shuffling of the x words
+          const uint32_t w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const double2 wq = *reinterpret_cast<const double2 *>(wp + 2 * (q ^ sw));  // features 2j, 2j+1, j = q ^ sw
+            const double2 wq = *reinterpret_cast<const double2 *>(wp + 2 * (q ^ sw));  // features 2q, 2q+1 of this chunk
             p0a = fma((double)__uint_as_float(w0[q] << 16), wq.x, p0a);
             p0b = fma((double)__uint_as_float(w0[q] & 0xffff0000u), wq.y, p0b);
             p1a = fma((double)__uint_as_float(w1[q] << 16), wq.x, p1a);
