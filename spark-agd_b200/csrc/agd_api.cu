@@ -114,7 +114,8 @@ struct Dev {
 
 struct agd_handle {
   std::vector<Dev> devs;
-  int32_t d = 0;
+  int32_t d = 0;       // INTERNAL dimension: d_user padded with zero columns so that rows are whole 16-byte vectors
+  int32_t d_user = 0;  // the caller's feature count (what agd_dim reports)
   int world = 1, first_rank = 0;
   bool comm_ready = false;
   int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised, 4 tcgen05 (bf16)
@@ -218,11 +219,23 @@ int ensure_slabs(agd_handle *h, Dev &D, int blocks, int32_t d) {
   return 0;
 }
 
-int set_dim(agd_handle *h, int32_t d) {
+// elem_bytes > 0: dense storage -- rows are padded with zero columns to whole 16-byte vectors when that puts the
+// shard on the TMA-ring / tcgen05 kernels.  The solver then runs in the padded dimension, which is bit-identical:
+// the extra gradient entries are exactly 0, so the extra weights stay exactly 0 under every updater.
+int set_dim(agd_handle *h, int32_t d, int elem_bytes = 0) {
   std::lock_guard<std::mutex> g(h->mu);
   if (d <= 0) return fail(h, "feature dimension must be positive (got %d)", d);
-  if (h->d == 0) h->d = d;
-  else if (h->d != d) return fail(h, "feature dimension mismatch: shard has d=%d, call passed d=%d", h->d, d);
+  if (h->d_user == 0) {
+    h->d_user = d;
+    h->d = d;
+    if (elem_bytes > 0) {
+      const int epv = 16 / elem_bytes;
+      const int padded = (d + epv - 1) / epv * epv;
+      if (padded != d && k1_ring_supported(padded, elem_bytes)) h->d = padded;
+    }
+  } else if (h->d_user != d) {
+    return fail(h, "feature dimension mismatch: shard has d=%d, call passed d=%d", h->d_user, d);
+  }
   return 0;
 }
 
@@ -704,10 +717,10 @@ int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t
 int agd_reserve(agd_handle *h, int32_t dev, int64_t rows_capacity, int32_t d, int32_t store_dtype) {
   if (!h) return 1;
   if (dev < 0 || dev >= (int)h->devs.size()) return fail(h, "bad local device index %d", dev);
-  if (set_dim(h, d)) return 1;
+  if (set_dim(h, d, dtype_bytes(store_dtype))) return 1;
   Dev &D = h->devs[dev];
   std::lock_guard<std::mutex> g(*D.mu);
-  return reserve_locked(h, D, rows_capacity, d, store_dtype);
+  return reserve_locked(h, D, rows_capacity, h->d, store_dtype);
 }
 
 int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype, const double *labels,
@@ -718,22 +731,23 @@ int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype,
   if (sb != 4 && sb != 8) return fail(h, "src_dtype must be AGD_F32 or AGD_F64");
   if (rows < 0 || ld < d) return fail(h, "bad geometry rows=%lld d=%d ld=%lld", (long long)rows, d, (long long)ld);
   if (rows > 0 && (!X || !labels)) return fail(h, "NULL data pointer");
-  if (set_dim(h, d)) return 1;
+  if (set_dim(h, d, dtype_bytes(store_dtype))) return 1;
+  const int32_t di = h->d;  // stored row length (>= d, zero-padded)
   Dev &D = h->devs[dev];
   std::lock_guard<std::mutex> g(*D.mu);
   Shard &s = D.sh;
   const int64_t need = s.rows + rows;
   if (s.cap == 0 || need > s.cap) {
     const int64_t cap = s.cap == 0 ? need : (need > 2 * s.cap ? need : 2 * s.cap);
-    if (reserve_locked(h, D, cap, d, s.cap ? bytes_dtype(s.elem_bytes) : store_dtype)) return 1;
+    if (reserve_locked(h, D, cap, di, s.cap ? bytes_dtype(s.elem_bytes) : store_dtype)) return 1;
   }
   const int eb = s.elem_bytes;
   if (dtype_bytes(store_dtype) != eb) return fail(h, "storage dtype mismatch with the resident shard");
   CK(cudaSetDevice(D.ordinal));
-  unsigned char *dst = (unsigned char *)s.X + (size_t)s.rows * d * eb;
+  unsigned char *dst = (unsigned char *)s.X + (size_t)s.rows * di * eb;
   const unsigned char *src = (const unsigned char *)X;
   if (rows > 0) {
-    if (sb == eb && ld == d) {
+    if (sb == eb && ld == d && di == d) {
       CK(cudaMemcpyAsync(dst, src, (size_t)rows * d * eb, cudaMemcpyHostToDevice, D.st));
     } else {
       int64_t chunk = (int64_t)((64u << 20) / ((size_t)ld * sb));
@@ -743,7 +757,7 @@ int agd_load_dense(agd_handle *h, int32_t dev, const void *X, int32_t src_dtype,
       for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
         const int64_t rc = rows - r0 < chunk ? rows - r0 : chunk;
         CK(cudaMemcpyAsync(D.stage_dev, src + (size_t)r0 * ld * sb, (size_t)rc * ld * sb, cudaMemcpyHostToDevice, D.st));
-        CK(convert_rows_launch(dst + (size_t)r0 * d * eb, eb, D.stage_dev, sb, rc, d, ld, D.st));
+        CK(convert_rows_launch(dst + (size_t)r0 * di * eb, eb, D.stage_dev, sb, rc, d, ld, di, D.st));
         CK(cudaStreamSynchronize(D.st));  // the staging buffer is reused
       }
     }
@@ -827,7 +841,7 @@ int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_
     } else {
       unsigned char *stage_vals = (unsigned char *)D.stage_dev + (((size_t)rows + 1) * sizeof(int64_t) + 63) / 64 * 64;
       CK(cudaMemcpyAsync(stage_vals, val, (size_t)nnz * sb, cudaMemcpyHostToDevice, D.st));
-      CK(convert_rows_launch((unsigned char *)s.val + (size_t)s.nnz * eb, eb, stage_vals, sb, nnz, 1, 1, D.st));
+      CK(convert_rows_launch((unsigned char *)s.val + (size_t)s.nnz * eb, eb, stage_vals, sb, nnz, 1, 1, 1, D.st));
     }
   }
   CK(cudaStreamSynchronize(D.st));
@@ -896,6 +910,7 @@ int agd_clear(agd_handle *h) {
     if (free_shard(h, D)) return 1;
   }
   h->d = 0;
+  h->d_user = 0;
   return 0;
 }
 
@@ -903,7 +918,7 @@ int64_t agd_rows(const agd_handle *h, int32_t dev) {
   if (!h || dev < 0 || dev >= (int)h->devs.size()) return -1;
   return h->devs[dev].sh.rows;
 }
-int32_t agd_dim(const agd_handle *h) { return h ? h->d : 0; }
+int32_t agd_dim(const agd_handle *h) { return h ? h->d_user : 0; }
 
 int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dtype, uint64_t seed, int32_t gradient) {
   if (!h) return 1;
@@ -911,19 +926,21 @@ int agd_generate(agd_handle *h, int64_t total_rows, int32_t d, int32_t store_dty
   if (!eb) return fail(h, "store_dtype must be AGD_F64, AGD_F32 or AGD_BF16");
   if (total_rows < 0) return fail(h, "negative row count");
   if (agd_clear(h)) return 1;
-  if (set_dim(h, d)) return 1;
+  if (set_dim(h, d, eb)) return 1;
+  const int32_t di = h->d;
   for (size_t i = 0; i < h->devs.size(); ++i) {
     Dev &D = h->devs[i];
     std::lock_guard<std::mutex> g(*D.mu);
     const long long rank = h->first_rank + (long long)i, W = h->world;
     const int64_t lo = (int64_t)(((__int128)rank * total_rows) / W), hi = (int64_t)(((__int128)(rank + 1) * total_rows) / W);
-    if (reserve_locked(h, D, hi - lo, d, store_dtype)) return 1;
-    if (ensure_vectors(h, D, d)) return 1;
+    if (reserve_locked(h, D, hi - lo, di, store_dtype)) return 1;
+    if (ensure_vectors(h, D, di)) return 1;
     CK(cudaSetDevice(D.ordinal));
     D.row_base = lo;
-    CK(synth_dense_launch(D.sh.X, eb, seed, lo, hi - lo, d, D.st));
+    CK(synth_dense_launch(D.sh.X, eb, seed, lo, hi - lo, d, di, D.st));
     CK(synth_wtrue_launch(D.wtmp, seed, d, D.st));
-    CK(synth_labels_launch(D.sh.X, eb, D.wtmp, D.sh.labels, seed, gradient, lo, hi - lo, d, D.st));
+    CK(synth_labels_launch(D.sh.X, eb, D.wtmp, D.sh.labels, seed, gradient, lo, hi - lo, d, di, D.st));
+    CK(cudaMemsetAsync(D.wtmp, 0, ((size_t)di + 2) * sizeof(double), D.st));
     D.sh.rows = hi - lo;
   }
   for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
@@ -938,8 +955,8 @@ int agd_get_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, void *X
   if (s.csr) return fail(h, "agd_get_rows serves dense shards only");
   if (row0 < 0 || rows < 0 || row0 + rows > s.rows) return fail(h, "row range out of bounds");
   CK(cudaSetDevice(D.ordinal));
-  const size_t rb = (size_t)h->d * s.elem_bytes;
-  if (X_out && rows) CK(cudaMemcpyAsync(X_out, (const unsigned char *)s.X + (size_t)row0 * rb, (size_t)rows * rb, cudaMemcpyDeviceToHost, D.st));
+  const size_t rb = (size_t)h->d * s.elem_bytes, ub = (size_t)h->d_user * s.elem_bytes;  // stored / user row bytes
+  if (X_out && rows) CK(cudaMemcpy2DAsync(X_out, ub, (const unsigned char *)s.X + (size_t)row0 * rb, rb, ub, (size_t)rows, cudaMemcpyDeviceToHost, D.st));
   if (labels_out && rows) CK(cudaMemcpyAsync(labels_out, s.labels + row0, (size_t)rows * sizeof(double), cudaMemcpyDeviceToHost, D.st));
   CK(cudaStreamSynchronize(D.st));
   return 0;
@@ -991,7 +1008,8 @@ int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, d
   const int32_t d = h->d;
   for (Dev &D : h->devs) {
     CK(cudaSetDevice(D.ordinal));
-    CK(cudaMemcpyAsync(D.wtmp, w, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, D.st));  // = broadcast, AGD.scala:193
+    CK(cudaMemsetAsync(D.wtmp, 0, ((size_t)d + 2) * sizeof(double), D.st));                            // zero weights on padded columns
+    CK(cudaMemcpyAsync(D.wtmp, w, (size_t)h->d_user * sizeof(double), cudaMemcpyHostToDevice, D.st));  // = broadcast, AGD.scala:193
   }
   h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
   h->launches = h->collectives = 0;
@@ -1003,7 +1021,7 @@ int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, d
   for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
   const double cnt = host[(size_t)d + 1];
   *loss = host[d] / cnt;                                    // AGD.scala:207
-  for (int32_t j = 0; j < d; ++j) grad[j] = host[j] / cnt;
+  for (int32_t j = 0; j < h->d_user; ++j) grad[j] = host[j] / cnt;
   if (count) *count = (int64_t)cnt;
   return 0;
 }
@@ -1052,7 +1070,8 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
 
   for (Dev &D : h->devs) {                                                 // :224-225  x = w0 ; z = x
     CK(cudaSetDevice(D.ordinal));
-    CK(cudaMemcpyAsync(D.x, w0, vb, cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemsetAsync(D.x, 0, vb, D.st));  // padded columns carry zero weights throughout
+    CK(cudaMemcpyAsync(D.x, w0, (size_t)h->d_user * sizeof(double), cudaMemcpyHostToDevice, D.st));
     CK(k3_copy2_launch(D.z, D.x, nullptr, nullptr, d, D.st));
   }
   h->launches += 1;
@@ -1176,7 +1195,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   {
     Dev &D = h->devs[0];
     CK(cudaSetDevice(D.ordinal));
-    CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));    // :337
+    CK(cudaMemcpyAsync(w_out, D.x, (size_t)h->d_user * sizeof(double), cudaMemcpyDeviceToHost, D.st));    // :337
   }
   if (call_end(h, s, t_begin)) return 1;
   for (int k = 0; k < nh; ++k)                                             // :306 for the deferred f_x values
@@ -1228,7 +1247,8 @@ int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, doubl
   };
   for (Dev &D : h->devs) {
     CK(cudaSetDevice(D.ordinal));
-    CK(cudaMemcpyAsync(D.x, w0, vb, cudaMemcpyHostToDevice, D.st));
+    CK(cudaMemsetAsync(D.x, 0, vb, D.st));  // padded columns carry zero weights throughout
+    CK(cudaMemcpyAsync(D.x, w0, (size_t)h->d_user * sizeof(double), cudaMemcpyHostToDevice, D.st));
     CK(cudaMemsetAsync(D.g_x, 0, vb, D.st));
   }
   // regVal = updater.compute(weights, zeros, 0, 1, regParam)._2
@@ -1255,7 +1275,7 @@ int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, doubl
   {
     Dev &D = h->devs[0];
     CK(cudaSetDevice(D.ordinal));
-    CK(cudaMemcpyAsync(w_out, D.x, vb, cudaMemcpyDeviceToHost, D.st));
+    CK(cudaMemcpyAsync(w_out, D.x, (size_t)h->d_user * sizeof(double), cudaMemcpyDeviceToHost, D.st));
   }
   if (call_end(h, s, t_begin)) return 1;
   *n_hist = nh;

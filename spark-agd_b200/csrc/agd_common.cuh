@@ -127,11 +127,11 @@ cudaError_t k3_prox_launch(const K3ProxArgs &a, cudaStream_t st);
 int k3_blocks(int32_t d);
 
 // ---------------------------------------------------------------- K0: synthetic workload (harness)
-cudaError_t synth_dense_launch(void *X, int elem_bytes, uint64_t seed, int64_t row0, int64_t rows, int32_t d,
+cudaError_t synth_dense_launch(void *X, int elem_bytes, uint64_t seed, int64_t row0, int64_t rows, int32_t d, int32_t ld,
                                cudaStream_t st);
 cudaError_t synth_wtrue_launch(double *w, uint64_t seed, int32_t d, cudaStream_t st);
 cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_true, double *labels, uint64_t seed,
-                                int kind, int64_t row0, int64_t rows, int32_t d, cudaStream_t st);
+                                int kind, int64_t row0, int64_t rows, int32_t d, int32_t ld, cudaStream_t st);
 
 cudaError_t synth_csr_launch(int64_t *rowptr, int32_t *idx, void *val, int elem_bytes, const double *w_true,
                              double *labels, uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, int32_t k,
@@ -141,8 +141,8 @@ cudaError_t synth_csr_launch(int64_t *rowptr, int32_t *idx, void *val, int elem_
 cudaError_t csr_shift_rowptr_launch(int64_t *dst, const int64_t *src, int64_t n, int64_t shift, cudaStream_t st);
 
 // ---------------------------------------------------------------- load path
-// dst (store dtype, ld == d) <- src (src dtype, leading dimension ld), rows x d
+// dst (store dtype, rows x dst_ld, columns >= d zero) <- src (src dtype, leading dimension ld), rows x d
 cudaError_t convert_rows_launch(void *dst, int dst_bytes, const void *src, int src_bytes, int64_t rows, int32_t d,
-                                int64_t ld, cudaStream_t st);
+                                int64_t ld, int32_t dst_ld, cudaStream_t st);
 
 }  // namespace agd

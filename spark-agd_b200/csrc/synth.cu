@@ -47,8 +47,9 @@ template <> __device__ __forceinline__ __nv_bfloat16 convert_elem<__nv_bfloat16,
 __device__ __forceinline__ float synth_x_scale() { return (float)(1.7320508075688772 / 65536.0); }
 
 template <typename T>
-__global__ void __launch_bounds__(256) synth_dense_kernel(T *X, uint64_t seed, long long row0, long long rows, int d) {
-  const int pairs = (d + 1) / 2;
+__global__ void __launch_bounds__(256) synth_dense_kernel(T *X, uint64_t seed, long long row0, long long rows, int d,
+                                                         int ld) {
+  const int pairs = (ld + 1) / 2;  // columns >= d (row padding) are written as zeros
   const long long total = rows * (long long)pairs;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const float scale = synth_x_scale();
@@ -60,9 +61,9 @@ __global__ void __launch_bounds__(256) synth_dense_kernel(T *X, uint64_t seed, l
     philox4x32_10(k0, k1, (uint32_t)i, (uint32_t)(i >> 32), (uint32_t)jp, 1u, o);
     const float x0 = __fmul_rn((float)irwin_hall4(o[0], o[1]), scale);
     const float x1 = __fmul_rn((float)irwin_hall4(o[2], o[3]), scale);
-    T *row = X + (size_t)r * d;
-    row[2 * jp] = from_f32<T>(x0);  // bf16 storage: the fp32 spec value rounded to nearest-even
-    if (2 * jp + 1 < d) row[2 * jp + 1] = from_f32<T>(x1);
+    T *row = X + (size_t)r * ld;
+    if (2 * jp < ld) row[2 * jp] = from_f32<T>(2 * jp < d ? x0 : 0.f);  // bf16 storage: the fp32 spec value rounded to nearest-even
+    if (2 * jp + 1 < ld) row[2 * jp + 1] = from_f32<T>(2 * jp + 1 < d ? x1 : 0.f);
   }
 }
 
@@ -78,12 +79,12 @@ __global__ void synth_wtrue_kernel(double *w, uint64_t seed, int d) {
 template <typename T>
 __global__ void __launch_bounds__(256) synth_labels_kernel(const T *X, const double *w_true, double *labels,
                                                           uint64_t seed, int kind, long long row0, long long rows,
-                                                          int d) {
+                                                          int d, int ld) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * 256LL + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * 256LL) >> 5;
   for (long long r = warp_global; r < rows; r += nwarps) {
-    const T *row = X + (size_t)r * d;
+    const T *row = X + (size_t)r * ld;
     double m = 0.0;
     for (int j = lane; j < d; j += 32) m = fma(to_f64<T>(row[j]), w_true[j], m);
     for (int off = 16; off >= 1; off >>= 1) m += __shfl_xor_sync(0xffffffffu, m, off);
@@ -160,13 +161,15 @@ __global__ void __launch_bounds__(256) synth_csr_labels_kernel(const long long *
   }
 }
 
+// dst (rows x dst_ld, columns >= d zero-filled) <- src (rows x d, leading dimension ld)
 template <typename D, typename S>
-__global__ void __launch_bounds__(256) convert_rows_kernel(D *dst, const S *src, long long rows, int d, long long ld) {
-  const long long total = rows * (long long)d;
+__global__ void __launch_bounds__(256) convert_rows_kernel(D *dst, const S *src, long long rows, int d, long long ld,
+                                                          int dst_ld) {
+  const long long total = rows * (long long)dst_ld;
   for (long long q = blockIdx.x * 256LL + threadIdx.x; q < total; q += (long long)gridDim.x * 256LL) {
-    const long long r = q / d;
-    const int j = (int)(q - r * d);
-    dst[q] = convert_elem<D, S>(src[r * ld + j]);
+    const long long r = q / dst_ld;
+    const int j = (int)(q - r * dst_ld);
+    dst[q] = j < d ? convert_elem<D, S>(src[r * ld + j]) : convert_elem<D, S>((S)0);
   }
 }
 
@@ -183,16 +186,16 @@ inline unsigned grid_for(long long total) {
 
 }  // namespace
 
-cudaError_t synth_dense_launch(void *X, int elem_bytes, uint64_t seed, int64_t row0, int64_t rows, int32_t d,
+cudaError_t synth_dense_launch(void *X, int elem_bytes, uint64_t seed, int64_t row0, int64_t rows, int32_t d, int32_t ld,
                                cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const long long total = rows * (long long)((d + 1) / 2);
+  const long long total = rows * (long long)((ld + 1) / 2);
   if (elem_bytes == 2)
-    synth_dense_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>((__nv_bfloat16 *)X, seed, row0, rows, d);
+    synth_dense_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>((__nv_bfloat16 *)X, seed, row0, rows, d, ld);
   else if (elem_bytes == 4)
-    synth_dense_kernel<float><<<grid_for(total), 256, 0, st>>>((float *)X, seed, row0, rows, d);
+    synth_dense_kernel<float><<<grid_for(total), 256, 0, st>>>((float *)X, seed, row0, rows, d, ld);
   else
-    synth_dense_kernel<double><<<grid_for(total), 256, 0, st>>>((double *)X, seed, row0, rows, d);
+    synth_dense_kernel<double><<<grid_for(total), 256, 0, st>>>((double *)X, seed, row0, rows, d, ld);
   return cudaGetLastError();
 }
 
@@ -202,15 +205,15 @@ cudaError_t synth_wtrue_launch(double *w, uint64_t seed, int32_t d, cudaStream_t
 }
 
 cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_true, double *labels, uint64_t seed,
-                                int kind, int64_t row0, int64_t rows, int32_t d, cudaStream_t st) {
+                                int kind, int64_t row0, int64_t rows, int32_t d, int32_t ld, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = grid_for(rows * 32);
   if (elem_bytes == 2)
-    synth_labels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)X, w_true, labels, seed, kind, row0, rows, d);
+    synth_labels_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)X, w_true, labels, seed, kind, row0, rows, d, ld);
   else if (elem_bytes == 4)
-    synth_labels_kernel<float><<<grid, 256, 0, st>>>((const float *)X, w_true, labels, seed, kind, row0, rows, d);
+    synth_labels_kernel<float><<<grid, 256, 0, st>>>((const float *)X, w_true, labels, seed, kind, row0, rows, d, ld);
   else
-    synth_labels_kernel<double><<<grid, 256, 0, st>>>((const double *)X, w_true, labels, seed, kind, row0, rows, d);
+    synth_labels_kernel<double><<<grid, 256, 0, st>>>((const double *)X, w_true, labels, seed, kind, row0, rows, d, ld);
   return cudaGetLastError();
 }
 
@@ -238,21 +241,21 @@ cudaError_t synth_csr_launch(int64_t *rowptr, int32_t *idx, void *val, int elem_
 }
 
 cudaError_t convert_rows_launch(void *dst, int dst_bytes, const void *src, int src_bytes, int64_t rows, int32_t d,
-                                int64_t ld, cudaStream_t st) {
+                                int64_t ld, int32_t dst_ld, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const unsigned grid = grid_for(rows * (long long)d);
+  const unsigned grid = grid_for(rows * (long long)dst_ld);
   if (dst_bytes == 2 && src_bytes == 4)
-    convert_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((__nv_bfloat16 *)dst, (const float *)src, rows, d, ld);
+    convert_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((__nv_bfloat16 *)dst, (const float *)src, rows, d, ld, dst_ld);
   else if (dst_bytes == 2 && src_bytes == 8)
-    convert_rows_kernel<__nv_bfloat16, double><<<grid, 256, 0, st>>>((__nv_bfloat16 *)dst, (const double *)src, rows, d, ld);
+    convert_rows_kernel<__nv_bfloat16, double><<<grid, 256, 0, st>>>((__nv_bfloat16 *)dst, (const double *)src, rows, d, ld, dst_ld);
   else if (dst_bytes == 4 && src_bytes == 4)
-    convert_rows_kernel<float, float><<<grid, 256, 0, st>>>((float *)dst, (const float *)src, rows, d, ld);
+    convert_rows_kernel<float, float><<<grid, 256, 0, st>>>((float *)dst, (const float *)src, rows, d, ld, dst_ld);
   else if (dst_bytes == 4 && src_bytes == 8)
-    convert_rows_kernel<float, double><<<grid, 256, 0, st>>>((float *)dst, (const double *)src, rows, d, ld);
+    convert_rows_kernel<float, double><<<grid, 256, 0, st>>>((float *)dst, (const double *)src, rows, d, ld, dst_ld);
   else if (dst_bytes == 8 && src_bytes == 4)
-    convert_rows_kernel<double, float><<<grid, 256, 0, st>>>((double *)dst, (const float *)src, rows, d, ld);
+    convert_rows_kernel<double, float><<<grid, 256, 0, st>>>((double *)dst, (const float *)src, rows, d, ld, dst_ld);
   else
-    convert_rows_kernel<double, double><<<grid, 256, 0, st>>>((double *)dst, (const double *)src, rows, d, ld);
+    convert_rows_kernel<double, double><<<grid, 256, 0, st>>>((double *)dst, (const double *)src, rows, d, ld, dst_ld);
   return cudaGetLastError();
 }
 

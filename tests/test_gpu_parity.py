@@ -38,7 +38,7 @@ def rel_err(a, b):
 
 # ------------------------------------------------------------------ applySmooth (K1 + reduce)
 SHAPES = [(1000, 100), (10000, 2), (3001, 1024), (2000, 512), (515, 256), (260, 128), (777, 2048), (300, 4096),
-          (129, 1100), (10, 20000), (37, 36), (1, 1024), (7, 1024)]
+          (129, 1100), (10, 20000), (37, 36), (1, 1024), (7, 1024), (501, 1001), (300, 37), (64, 4095), (90, 3)]
 
 
 @pytest.mark.parametrize("grad", GRADS + ["least_squares_half"])
@@ -420,6 +420,8 @@ CASES = [
     (4000, 64, "logistic", "simple", 0.0, "f64", 20, {"may_restart": False}),
     (4000, 64, "least_squares", "simple", 0.0, "f64", 25, {"L0": 1e-3}),           # forces the L-increase branch
     (4000, 64, "least_squares", "simple", 0.0, "f64", 25, {"L0": 1e-3, "Lexact": 8.0}),
+    (6000, 1001, "logistic", "l1", 0.002, "f32", 12, {}),       # odd d: rows padded with zero columns at load
+    (3000, 37, "hinge", "squared_l2", 0.05, "f64", 12, {}),
 ]
 
 
@@ -480,6 +482,28 @@ def test_zero_iterations_returns_initial_weights(agd, ctx):
     w, hist, st = agd.run_with_stats(data, agd.LogisticGradient(), agd.SimpleUpdater(), 1e-4, 0, 0.0, [1, 2, 3, 4.0])
     assert len(hist) == 0 and np.array_equal(w, [1, 2, 3, 4.0])
     data.close()
+
+
+def test_padded_rows_are_invisible(agd, ctx, oracle):
+    """d = 1001 fp32 rows are stored as 1004 columns (whole 16-byte vectors, zero padding) so that the TMA-ring kernel
+    applies; the caller still sees d = 1001 everywhere and the ring and generic kernels agree."""
+    rng = np.random.default_rng(41)
+    X, y = make_data(rng, 2500, 1001, "logistic", np.float32)
+    w = rng.standard_normal(1001) * 0.05
+    ds = ctx.parallelize(y, X, store="f32")
+    assert ds.d == 1001
+    Xb, yb = ds.get_rows(0, 100, 50)
+    assert Xb.shape == (50, 1001) and np.array_equal(Xb, X[100:150]) and np.array_equal(yb, y[100:150])
+    a = ds.smooth(agd.LogisticGradient(), w)
+    ds.set_option("k1_variant", "generic")
+    b = ds.smooth(agd.LogisticGradient(), w)
+    assert a[1].shape == (1001,) and a[2] == b[2] == 2500
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-13)
+    assert rel_err(a[1], b[1]) < 1e-13
+    ds.set_option("k1_variant", "ring")          # would have been rejected before: 1001 * 4 bytes is not a multiple of 16
+    c = ds.smooth(agd.LogisticGradient(), w)
+    assert c[0] == a[0] and np.array_equal(c[1], a[1])
+    ds.close()
 
 
 def test_argument_errors(agd, ctx):
