@@ -214,8 +214,8 @@ def run_b200(args):
         args.no_e2e = True
         args.no_cpu_baseline = True
 
-    def run(ds, iters, memoize=False):
-        return S.run_with_stats(ds, grad, upd, 0.0, iters, reg, w0, memoize=memoize)
+    def run(ds, iters, memoize=False, fuse=True):
+        return S.run_with_stats(ds, grad, upd, 0.0, iters, reg, w0, memoize=memoize, fuse=fuse)
 
     # ---- warm-up, then EXACTLY K timed steps, barrier + synchronize on both sides
     barrier()
@@ -234,10 +234,19 @@ def run_b200(args):
     barrier()
     _, _, st_m = run(data, args.steps, memoize=True)
     dev_s_m = max_over_ranks(st_m.device_ms_total / 1e3)
+    # every evaluation as a sweep of its own (AGD_FLAG_NO_FUSE): the same results bit for bit, one more read of X per iteration
+    barrier()
+    _, hist_u, st_u = run(data, args.steps, fuse=False)
+    dev_s_u = max_over_ranks(st_u.device_ms_total / 1e3)
+    if wl != "hinge_csr":       # (CSR sums are atomics: reproducible to rounding only)
+        assert np.array_equal(hist_u, hist), "fused and unfused runs must agree bit for bit"
 
     # ---- roofline of the dominant kernel (K1), CUDA events on its own stream inside the timed region
     peak, peak_src = peaks()
     k1_ms = st.k1_ms_total / max(st.k1_launches, 1)
+    k1_ms_single = st_u.k1_ms_total / max(st_u.k1_launches, 1)          # one point per sweep
+    n_two = st.fused_passes
+    k1_ms_two = (st.k1_ms_total - (st.k1_launches - n_two) * k1_ms_single) / n_two if n_two else None
     if wl == "hinge_csr":
         alg_bytes = rows_local * (args.nnz * (4 + eb) + 16)   # idx + value per entry, rowptr + label per row
     else:
@@ -248,6 +257,9 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows_local, d) if wl == "logistic_f32" else None,
                 "peak_source": peak_src, "bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
+                "launches": int(st.k1_launches), "two_point_launches": int(n_two),
+                "ms_per_launch_one_point": k1_ms_single, "ms_per_launch_two_point": k1_ms_two,
+                "frac_one_point": alg_bytes / (k1_ms_single * 1e-3) / 1e9 / peak,
                 "k1_share_of_step": st.k1_ms_total / st.device_ms_total}
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N = 1 only
@@ -278,11 +290,20 @@ def run_b200(args):
                                     "hinge_csr": f"hinge-loss + L2 (reg 0.1) AGD, {total_rows} x {d} CSR, {args.nnz} stored entries per "
                                                  f"row (BASELINE configs[2] shape)"}[wl],
                        "rows": total_rows, "d": d, "store": store, "rows_per_gpu": rows_local,
-                       "parallelism": f"row shards x{world}, one all-reduce of d+2 fp64 per pass",
+                       "parallelism": f"row shards x{world}, one all-reduce of d+4 fp64 per sweep",
+                       "accounting": "value = rows x applySmooth evaluations / s (the reference's unit of work, 3 + 2b per "
+                                     "iteration, AGD.scala:250,269,304); `fused_passes` of them shared a sweep over X with the next "
+                                     "iteration's first evaluation, `sweeps` is the number of reads of X, `physical_examples_per_sec` "
+                                     "counts those reads instead; `unfused` runs every evaluation as its own sweep",
                        "l2": "inputs larger than L2: every pass streams the whole shard "
                              f"({alg_bytes / 1e9:.2f} GB) from HBM"},
             "iters_per_sec": st.iterations / dev_s, "passes": st.passes, "passes_per_iter": st.passes / st.iterations,
+            "fused_passes": int(st.fused_passes), "sweeps": int(st.k1_launches),
+            "physical_examples_per_sec": total_rows * st.k1_launches / dev_s,
             "backtracks": st.backtracks, "restarts": st.restarts, "final_loss": float(hist[-1]),
+            "unfused": {"iters_per_sec": st_u.iterations / dev_s_u, "examples_per_sec": total_rows * st_u.passes / dev_s_u,
+                        "sweeps": int(st_u.k1_launches),
+                        "note": "AGD_FLAG_NO_FUSE: same weights and history bit for bit, 3 + 2b reads of X per iteration"},
             "memoized": {"iters_per_sec": st_m.iterations / dev_s_m, "passes_per_iter": st_m.passes / st_m.iterations,
                          "examples_per_sec": total_rows * st_m.passes / dev_s_m,
                          "note": "AGD_FLAG_MEMOIZE_FX: same weights and history bit for bit, fewer passes"},

@@ -42,6 +42,10 @@ enum { AGD_F64 = 0, AGD_F32 = 1, AGD_BF16 = 2 };
 enum {
   AGD_FLAG_MEMOIZE_FX = 1, /* reuse (f_x, g_x) of AGD.scala:269 for the history pass at :304 when x is
                               unchanged (bit-identical result, 3 -> 2 passes per iteration) */
+  AGD_FLAG_NO_FUSE = 2,    /* by default the history evaluation applySmooth(x) of AGD.scala:304 rides along with
+                              applySmooth(y) of the NEXT iteration (AGD.scala:250) in one sweep over the shards: the same
+                              evaluations and the same results bit for bit (dense shards), one read of X fewer per iteration.
+                              This flag runs every evaluation as a sweep of its own. */
 };
 
 /* The constructor arguments + eight hyper-parameters of AGD.scala:41-51 (defaults: agd_default_params). */
@@ -79,7 +83,7 @@ typedef struct {
   double device_ms_total;    /* CUDA events on device 0's stream around the whole call */
   int64_t collective_calls;  /* all-reduces enqueued per device */
   int32_t wasted_passes;     /* speculative applySmooth(x) passes discarded because ||x-y||^2 == 0 (AGD.scala:265) */
-  int32_t reserved1;
+  int32_t fused_passes;      /* applySmooth evaluations that shared a sweep over X with another one (sweeps = passes - fused_passes) */
 } agd_stats;
 
 /* ---- lifecycle ---- */
@@ -156,6 +160,12 @@ int agd_get_csr_rows(agd_handle *h, int32_t dev, int64_t row0, int64_t rows, int
  * agd_smooth = applySmooth (AGD.scala:192-208): loss/count and grad/count over ALL shards of the
  * world; w, grad are d doubles on the host.  Every rank must call it. */
 int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, double *grad, int64_t *count);
+/* agd_smooth at w plus the loss (no gradient) at a second point w2, both from ONE sweep over the shards -- the fused form of
+ * applySmooth(y) (AGD.scala:250) and the history evaluation applySmooth(x) (:304) that agd_run uses.  On dense shards every
+ * output equals, bit for bit, what two agd_smooth calls return.  Fails on shards whose kernel has no two-point form
+ * (tcgen05 bf16 path, d below one 16-row tile); agd_run then simply does not fuse. */
+int agd_smooth_pair(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
+                    int64_t *count, double *loss2);
 /* agd_prox = applyProjector (AGD.scala:214-222): Updater.compute(w, g, step, iter = 1, reg). */
 int agd_prox(agd_handle *h, int32_t updater, const double *w, const double *g, double step, double reg,
              int32_t d, double *w_out, double *reg_val);

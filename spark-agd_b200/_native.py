@@ -15,6 +15,7 @@ GRAD_LOGISTIC, GRAD_LEAST_SQUARES, GRAD_HINGE, GRAD_LEAST_SQUARES_HALF = 0, 1, 2
 UPD_SIMPLE, UPD_SQUARED_L2, UPD_L1 = 0, 1, 2
 F64, F32, BF16 = 0, 1, 2
 FLAG_MEMOIZE_FX = 1
+FLAG_NO_FUSE = 2
 
 
 class Params(C.Structure):
@@ -30,7 +31,7 @@ class Stats(C.Structure):
                 ("final_theta", C.c_double), ("seconds_total", C.c_double), ("k1_ms_total", C.c_double),
                 ("k1_launches", C.c_int64), ("gpu_launches", C.c_int64), ("allreduce_ms_total", C.c_double),
                 ("device_ms_total", C.c_double), ("collective_calls", C.c_int64), ("wasted_passes", C.c_int32),
-                ("reserved1", C.c_int32)]
+                ("fused_passes", C.c_int32)]
 
 
 def _sources():
@@ -95,6 +96,8 @@ _SIGNATURES = {
                                    C.c_int64, C.c_void_p]),
     "agd_smooth": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
                              C.POINTER(C.c_int64)]),
+    "agd_smooth_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "agd_prox": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
                            C.c_void_p, C.POINTER(C.c_double)]),
     "agd_run": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,

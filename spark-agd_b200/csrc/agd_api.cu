@@ -103,7 +103,7 @@ struct Dev {
   double *hist_host = nullptr;            // pinned: [2k] = loss sum, [2k+1] = count of the history pass of iteration k
   size_t hist_cap = 0;
   // K2' peer-memory exchange (xchg.cu)
-  double *xbuf = nullptr;                 // [2][W][d+2], written by every rank over NVLink
+  double *xbuf = nullptr;                 // [2][W][d+4], written by every rank over NVLink
   unsigned long long *xflags = nullptr;   // [2][W] epochs
   unsigned int *xticket = nullptr;
   XchgPeers xpeers;                       // every rank's xbuf / xflags as mapped into this device
@@ -197,11 +197,11 @@ int ensure_vectors(agd_handle *h, Dev &D, int32_t d) {
   for (double **p : v) {
     if (*p) cudaFree(*p);
     *p = nullptr;
-    CK(cudaMalloc(p, ((size_t)d + 2) * sizeof(double)));
-    CK(cudaMemsetAsync(*p, 0, ((size_t)d + 2) * sizeof(double), D.st));
+    CK(cudaMalloc(p, ((size_t)d + 4) * sizeof(double)));
+    CK(cudaMemsetAsync(*p, 0, ((size_t)d + 4) * sizeof(double), D.st));
   }
   if (D.acc) cudaFree(D.acc);
-  CK(cudaMalloc(&D.acc, ((size_t)d + 2) * sizeof(double)));
+  CK(cudaMalloc(&D.acc, ((size_t)d + 4) * sizeof(double)));  // [grad(d) | loss | count | loss at w2 | count at w2]
   if (D.partials) cudaFree(D.partials);
   CK(cudaMalloc(&D.partials, (size_t)k3_blocks(d) * K3_NS * sizeof(double)));
   D.vec_d = d;
@@ -209,7 +209,7 @@ int ensure_vectors(agd_handle *h, Dev &D, int32_t d) {
 }
 
 int ensure_slabs(agd_handle *h, Dev &D, int blocks, int32_t d) {
-  const size_t need = (size_t)blocks * ((size_t)d + 2);
+  const size_t need = (size_t)blocks * ((size_t)d + 4);
   if (need <= D.slabs_doubles) return 0;
   CK(cudaSetDevice(D.ordinal));
   if (D.slabs) cudaFree(D.slabs);
@@ -315,7 +315,7 @@ int ensure_xchg(agd_handle *h) {
   const int W = h->world, nd = (int)h->devs.size();
   if (W > kMaxRanks) { if (h->collective == 2) return fail(h, "peer exchange supports at most %d ranks", kMaxRanks); return 0; }
   NcclApi &N = nccl_api();
-  const size_t n = (size_t)h->d + 2;
+  const size_t n = (size_t)h->d + 4;
   struct Handles { cudaIpcMemHandle_t buf, flags; int can_peer; int pad[3]; };
   std::vector<Handles> mine(nd), all((size_t)W);
   // 1. allocate + export
@@ -423,17 +423,41 @@ int ensure_xchg(agd_handle *h) {
   return 0;
 }
 
+typedef const double *(*WSel)(Dev &);
+
+// which K1 kernel a dense shard of this handle runs on (0 generic, 1 ring, 2 warp-specialised, 3 tcgen05)
+int dense_kernel_of(const agd_handle *h, int eb) {
+  bool ring = k1_ring_supported(h->d, eb) != 0;
+  if (h->k1_variant == 2) ring = false;
+  if (k1_tc_supported(h->d, eb) && (h->k1_variant == 0 || h->k1_variant == 4)) return 3;
+  if (ring && h->k1_variant == 3) return 2;
+  return ring ? 1 : 0;
+}
+
+// can one sweep evaluate the loss at a second point as well (pass fusion)?
+bool dual_supported(const agd_handle *h) {
+  for (const Dev &D : h->devs) {
+    const Shard &s = D.sh;
+    if (s.csr) continue;
+    const int eb = s.elem_bytes ? s.elem_bytes : 4;
+    const int k = dense_kernel_of(h, eb);
+    if (k == 2 || k == 3) return false;
+    if (k == 1 && !k1_ring_dual_supported(h->d, eb)) return false;
+  }
+  return h->k1_diag == 0;
+}
+
 // One applySmooth (AGD.scala:192-208) at the device-resident point `w_of(dev)`: K1 over every local
-// shard, slab reduction, one all-reduce of [grad | loss | count].  Result: Dev::acc on every device.
-template <typename WSel>
-int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
+// shard, slab reduction, one all-reduce of [grad | loss | count | loss2 | count2].  Result: Dev::acc on every device.
+// w2_of != nullptr: the same sweep also evaluates the loss (not the gradient) at `w2_of(dev)` -> acc[d+2], acc[d+3].
+int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = nullptr) {
   const int32_t d = h->d;
   const bool p2p = h->world > 1 && h->x_p2p;
   const unsigned long long epoch = p2p ? ++h->x_epoch : 0ull;
   auto make_pub = [&](Dev &D, size_t i) {
     XchgPub pub;
     pub.peers = D.xpeers; pub.world = h->world; pub.my_rank = h->first_rank + (int)i; pub.buf = (int)(epoch & 1ull);
-    pub.n = d + 2; pub.epoch = epoch; pub.ticket = D.xticket;
+    pub.n = d + 4; pub.epoch = epoch; pub.ticket = D.xticket;
     return pub;
   };
   for (size_t i = 0; i < h->devs.size(); ++i) {
@@ -444,6 +468,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     if (s.csr) {
       K1CsrArgs a;
       a.rowptr = s.rowptr; a.idx = s.idx; a.val = s.val; a.labels = s.labels; a.w = w_of(D);
+      a.w2 = w2_of ? w2_of(D) : nullptr;
       a.gacc = D.acc; a.rows = s.rows; a.d = d; a.kind = kind;
       a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base;
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
@@ -454,8 +479,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
       continue;
     }
     K1Args a;
-    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
-    a.stages = h->ring_stages; a.slab_stride = d + 2;
+    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.w2 = w2_of ? w2_of(D) : nullptr; a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
+    a.stages = h->ring_stages; a.slab_stride = d + 4;
     a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     bool ring = k1_ring_supported(d, eb) != 0;
@@ -464,9 +489,11 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     const bool tc = k1_tc_supported(d, eb) && (h->k1_variant == 0 || h->k1_variant == 4);
     if (h->k1_variant == 4 && !tc) return fail(h, "tcgen05 kernel needs bf16 storage with d %% 128 == 0 and d <= 4096 (d=%d)", d);
     if ((h->k1_variant == 1 || h->k1_variant == 3) && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
+    if (a.w2 && (tc || ws || (ring && !k1_ring_dual_supported(d, eb))))
+      return fail(h, "internal: two-point sweep requested on a kernel without one");
     int max_blocks = k1_max_blocks(D.sm_count);
     if (!ring) {  // generic: bound the slab memory for very wide rows
-      const long long lim = (32LL << 20) / ((long long)d + 2);
+      const long long lim = (32LL << 20) / ((long long)d + 4);
       if (lim < max_blocks) max_blocks = lim < 1 ? 1 : (int)lim;
     }
     if (ensure_slabs(h, D, max_blocks, d)) return 1;
@@ -487,7 +514,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     for (Dev &D : h->devs) {
       CK(cudaSetDevice(D.ordinal));
-      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), d + 2, epoch, D.acc, D.st));
+      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), d + 4, epoch, D.acc, D.st));
     }
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     h->launches += 1;
@@ -498,7 +525,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed) {
     Dev &D0 = h->devs[0];
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     CKN(N.GroupStart());
-    for (Dev &D : h->devs) CKN(N.AllReduce(D.acc, D.acc, (size_t)d + 2, ncclDouble, ncclSum, D.comm, D.st));
+    for (Dev &D : h->devs) CKN(N.AllReduce(D.acc, D.acc, (size_t)d + 4, ncclDouble, ncclSum, D.comm, D.st));
     CKN(N.GroupEnd());
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     h->collectives += 1;
@@ -1002,28 +1029,48 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
 }
 
 // ---------------------------------------------------------------- applySmooth with host buffers
-int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, double *grad, int64_t *count) {
+static int smooth_host(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
+                       int64_t *count, double *loss2) {
   if (check_ready(h)) return 1;
   if (gradient < 0 || gradient > AGD_GRAD_LEAST_SQUARES_HALF) return fail(h, "unknown gradient %d", gradient);
+  if (!w || !loss || !grad) return fail(h, "NULL argument");
+  if (w2 && !dual_supported(h)) return fail(h, "this shard's gradient kernel has no two-point form (use two agd_smooth calls)");
   const int32_t d = h->d;
   for (Dev &D : h->devs) {
     CK(cudaSetDevice(D.ordinal));
     CK(cudaMemsetAsync(D.wtmp, 0, ((size_t)d + 2) * sizeof(double), D.st));                            // zero weights on padded columns
     CK(cudaMemcpyAsync(D.wtmp, w, (size_t)h->d_user * sizeof(double), cudaMemcpyHostToDevice, D.st));  // = broadcast, AGD.scala:193
+    if (w2) {
+      CK(cudaMemsetAsync(D.g_x, 0, ((size_t)d + 2) * sizeof(double), D.st));   // g_x doubles as the staging vector of w2
+      CK(cudaMemcpyAsync(D.g_x, w2, (size_t)h->d_user * sizeof(double), cudaMemcpyHostToDevice, D.st));
+    }
   }
   h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
   h->launches = h->collectives = 0;
-  if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.wtmp; }, false)) return 1;
+  if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.wtmp; }, false,
+                    w2 ? (WSel)[](Dev &D) { return (const double *)D.g_x; } : (WSel) nullptr))
+    return 1;
   Dev &D0 = h->devs[0];
   CK(cudaSetDevice(D0.ordinal));
-  std::vector<double> host((size_t)d + 2);
-  CK(cudaMemcpyAsync(host.data(), D0.acc, ((size_t)d + 2) * sizeof(double), cudaMemcpyDeviceToHost, D0.st));
+  std::vector<double> host((size_t)d + 4);
+  CK(cudaMemcpyAsync(host.data(), D0.acc, ((size_t)d + 4) * sizeof(double), cudaMemcpyDeviceToHost, D0.st));
   for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
   const double cnt = host[(size_t)d + 1];
   *loss = host[d] / cnt;                                    // AGD.scala:207
   for (int32_t j = 0; j < h->d_user; ++j) grad[j] = host[j] / cnt;
   if (count) *count = (int64_t)cnt;
+  if (w2 && loss2) *loss2 = host[(size_t)d + 2] / host[(size_t)d + 3];
   return 0;
+}
+
+int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, double *grad, int64_t *count) {
+  return smooth_host(h, gradient, w, nullptr, loss, grad, count, nullptr);
+}
+
+int agd_smooth_pair(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
+                    int64_t *count, double *loss2) {
+  if (h && (!w2 || !loss2)) return fail(h, "NULL argument");
+  return smooth_host(h, gradient, w, w2, loss, grad, count, loss2);
 }
 
 // ---------------------------------------------------------------- applyProjector with host buffers
@@ -1067,6 +1114,10 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   memset(&s, 0, sizeof s);
   if (call_begin(h)) return 1;
   const bool memoize = (p->flags & AGD_FLAG_MEMOIZE_FX) != 0;
+  // Pass fusion: the history evaluation applySmooth(x) (:304) of iteration k and applySmooth(y) (:250) of iteration k+1
+  // (first backtracking round) do not depend on each other, so ONE sweep over X evaluates both.
+  const bool fuse = (p->flags & AGD_FLAG_NO_FUSE) == 0 && dual_supported(h);
+  bool y_ready = false;   // acc already holds applySmooth(y) for the first round of the coming iteration
 
   for (Dev &D : h->devs) {                                                 // :224-225  x = w0 ; z = x
     CK(cudaSetDevice(D.ordinal));
@@ -1116,10 +1167,11 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       theta = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L / L_old) / (theta_old * theta_old)));  // :248
       const double omt = 1.0 - theta;
       if (first_round) {  // (x_old, z_old) = (x, z) :241 fused with y = x_old*(1-theta) + z_old*theta :249
-        if (launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt, theta, d, D.st); })) return 1;
+        if (!y_ready && launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt, theta, d, D.st); })) return 1;
         first_round = false;
       } else if (launch_all([&](Dev &D) { return k3_combine_launch(D.y, D.x_old, omt, D.z_old, theta, d, D.st); })) return 1;  // :249
-      if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
+      if (!y_ready && smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
+      y_ready = false;
       s.passes++;
       const double step = 1.0 / (theta * L);                               // :253
       if (launch_all([&](Dev &D) {                                         // :254-255,263-264 fused
@@ -1167,30 +1219,57 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     }
     const double c_x = reg_value(p->updater, p->reg_param, sc[2], sc[5]);  // :305  applyProjector(x, g_x, 0.0)._1
     cx_of.push_back(c_x);
-    if (!(memoize && have_fx)) {                                           // :304  (f_x, g_x) = applySmooth(x)
+    s.iterations = nIter;
+    // The exits of :309-324 and the restart of :327-331 depend on nothing the history evaluation (:304) produces, so they
+    // are decided first: when another iteration follows, that evaluation shares its sweep with the next applySmooth(y).
+    bool stop = false;
+    if (nonterminating) { s.stopped_nan = 1; s.nonterminating = 1; stop = true; }
+    else if (std::isnan(f_y) || std::isinf(f_y)) { s.stopped_nan = 1; stop = true; }  // :309-312
+    else {
+      const double norm_x = std::sqrt(sc[2]);                              // :315
+      const double norm_dx = std::sqrt(sc[3]);                             // :316
+      if (norm_dx == 0.0 && nIter > 1) { s.converged = 1; stop = true; }   // :317-321
+      else if (norm_dx < p->convergence_tol * jmax(norm_x, 1)) { s.converged = 1; stop = true; }  // :322-324
+    }
+    const bool restart = !stop && p->may_restart && sc[4] > 0.0;           // :327
+    const bool need_hist = !(memoize && have_fx);
+    const bool fuse_now = need_hist && fuse && !stop && nIter < p->num_iterations;
+    if (need_hist && !fuse_now) {                                          // :304  (f_x, g_x) = applySmooth(x)
       if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
       s.passes++;
       CK(cudaSetDevice(H0.ordinal));
       CK(cudaMemcpyAsync(H0.hist_host + 2 * (size_t)nh, H0.acc + d, 2 * sizeof(double), cudaMemcpyDeviceToHost, H0.st));
       fx_deferred.push_back(1);                                            // read after the loop
       loss_hist[nh++] = 0.0;
-    } else {
+    } else if (!need_hist) {
       fx_deferred.push_back(0);
       loss_hist[nh++] = f_x + c_x;                                         // :306
     }
-    s.iterations = nIter;
-    if (nonterminating) { s.stopped_nan = 1; s.nonterminating = 1; break; }
-    if (std::isnan(f_y) || std::isinf(f_y)) { s.stopped_nan = 1; break; }  // :309-312
-    const double norm_x = std::sqrt(sc[2]);                                // :315
-    const double norm_dx = std::sqrt(sc[3]);                               // :316
-    if (norm_dx == 0.0) { if (nIter > 1) { s.converged = 1; break; } }     // :317-321
-    if (norm_dx < p->convergence_tol * jmax(norm_x, 1)) { s.converged = 1; break; }  // :322-324
-    if (p->may_restart && sc[4] > 0.0) {                                   // :327
+    if (restart) {
       if (launch_all([&](Dev &D) { return k3_copy2_launch(D.z, D.x, nullptr, nullptr, d, D.st); })) return 1;  // :328
       theta = INF;                                                         // :329
       backtrack_simple = true;                                             // :330
       s.restarts++;
     }
+    if (fuse_now) {
+      // :243-249 of iteration nIter + 1, first round (the loop head recomputes the same doubles), then one sweep:
+      // acc[0..d+1] = applySmooth(y) sums, acc[d+2..d+3] = loss sum / count at x
+      const double L_n = L * p->alpha;
+      const double theta_n = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L_n / L) / (theta * theta)));
+      const double omt_n = 1.0 - theta_n;
+      if (launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt_n, theta_n, d, D.st); })) return 1;
+      if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true,
+                        [](Dev &D) { return (const double *)D.x; }))
+        return 1;
+      s.passes++;          // the history evaluation; the applySmooth(y) half is counted by the next iteration
+      s.fused_passes++;
+      y_ready = true;
+      CK(cudaSetDevice(H0.ordinal));
+      CK(cudaMemcpyAsync(H0.hist_host + 2 * (size_t)nh, H0.acc + d + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, H0.st));
+      fx_deferred.push_back(1);
+      loss_hist[nh++] = 0.0;
+    }
+    if (stop) break;
   }
   {
     Dev &D = h->devs[0];

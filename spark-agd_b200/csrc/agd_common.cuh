@@ -13,12 +13,13 @@ struct K1Args {
   const void *X;          // shard, row-major, ld == d, element type float or double
   const double *labels;   // rows (+ padding)
   const double *w;        // d doubles (device)
-  double *slabs;          // [grid][d + 2]: per-block column sums of loss' * x, the loss sum, the row count
+  const double *w2;       // optional second point of a fused sweep (AGD.scala:304 riding along with :250): loss only
+  double *slabs;          // [grid][d + 4]: per-block column sums of loss' * x, the loss sum, the row count at w; loss sum, count at w2
   int64_t rows;           // rows in the shard
   int32_t d;
   int32_t kind;           // AGD_GRAD_*
   int32_t stages;         // smem ring depth
-  int32_t slab_stride;    // d + 2
+  int32_t slab_stride;    // d + 4
   unsigned long long sample_seed, sample_thresh;  // Bernoulli row mask (thresh 0 = every row), see row_selected()
   long long row_base;     // global index of the shard's first row
   int32_t tune_rows;      // 0 = default; rows per tile of the headline ring shape (4|8)
@@ -27,6 +28,7 @@ struct K1Args {
 
 // launch helpers (k1_dense.cu); return the number of blocks that wrote a slab
 int k1_ring_supported(int32_t d, int elem_bytes);
+int k1_ring_dual_supported(int32_t d, int elem_bytes);
 cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
 cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
 cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
@@ -56,7 +58,8 @@ cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStrea
 cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
                                unsigned long long epoch, double *acc_out, cudaStream_t st);
 
-// out[c] = sum_b slabs[b][c] for c <= d + 1 (gradient sums, loss sum, row count; fixed order => deterministic);
+// out[c] = sum_b slabs[b][c] for c <= d + 3 (gradient sums, loss sum, row count, loss sum and count at w2; fixed order =>
+// deterministic);
 // with pub != nullptr the sums are also stored into every peer's exchange slot and the epoch flag is raised
 cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, const XchgPub *pub,
                              cudaStream_t st);
@@ -68,7 +71,8 @@ struct K1CsrArgs {
   const void *val;        // float or double
   const double *labels;
   const double *w;
-  double *gacc;           // d + 2 doubles, zeroed by the launch: gradient sum, loss sum, count
+  const double *w2;       // optional second point (loss only), as in K1Args
+  double *gacc;           // d + 4 doubles, zeroed by the launch: gradient sum, loss sum, count; loss sum, count at w2
   int64_t rows;
   int32_t d;
   int32_t kind;

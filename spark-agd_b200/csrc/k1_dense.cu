@@ -99,23 +99,27 @@ __host__ __device__ inline uint32_t round_up_u32(uint32_t v, uint32_t a) { retur
 
 // shared-memory carve-up (identical on host and device)
 struct RingLayout {
-  uint32_t stage_stride, aux_off, partial_off, mult_off, red_off, cnt_off, bars_off, total;
+  uint32_t stage_stride, aux_off, aux2_off, partial_off, partial2_off, mult_off, red_off, cnt_off, bars_off, total;
 };
-__host__ __device__ inline RingLayout ring_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages) {
+// dual = the launch also evaluates the loss at a second point w2 (pass fusion): a second w staging area and a second
+// set of per-warp partial dots
+__host__ __device__ inline RingLayout ring_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages, bool dual) {
   RingLayout L;
   L.stage_stride = round_up_u32(tile_bytes, 128);
   L.aux_off = L.stage_stride * stages;
-  L.partial_off = L.aux_off + round_up_u32(aux_bytes, 128);
-  L.mult_off = L.partial_off + kMaxTileRows * 8 * 8;
+  L.aux2_off = L.aux_off + round_up_u32(aux_bytes, 128);
+  L.partial_off = L.aux2_off + (dual ? round_up_u32(aux_bytes, 128) : 0u);
+  L.partial2_off = L.partial_off + kMaxTileRows * 8 * 8;
+  L.mult_off = L.partial2_off + (dual ? kMaxTileRows * 8 * 8 : 0);
   L.red_off = L.mult_off + kMaxTileRows * 8;
-  L.cnt_off = L.red_off + 16 * 8;
+  L.cnt_off = L.red_off + 32 * 8;
   L.bars_off = L.cnt_off + round_up_u32(stages * 4, 8);
   L.total = L.bars_off + (stages + 1) * 8;
   return L;
 }
 
 // ---------------------------------------------------------------- the hot kernel
-template <typename T, int NT, int TPR, int V, int R, int MINB>
+template <typename T, int NT, int TPR, int V, int R, int MINB, bool DUAL>
 __global__ void __launch_bounds__(NT, MINB)
 k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uint32_t aux_bytes) {
   constexpr int EPV = Elem<T>::EPV;
@@ -124,13 +128,17 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
   constexpr int TR = NG * R;            // rows per tile
   constexpr int NW = NT / 32;
   static_assert(TR <= kMaxTileRows && TR % 2 == 0 && (NW & (NW - 1)) == 0, "tile rows / warps");
+  // DUAL: lanes 0-15 of the scalar warp evaluate the rows at w, lanes 16-31 the same rows at w2
+  static_assert(!DUAL || TR <= 16, "pass fusion needs the tile's rows twice in one warp");
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int S = a.stages;
   const uint32_t row_bytes = (uint32_t)a.d * (uint32_t)sizeof(T);
-  const RingLayout L = ring_layout(TR * row_bytes + kMaxTileRows * 8, aux_bytes, S);  // rows, then their labels
+  const RingLayout L = ring_layout(TR * row_bytes + kMaxTileRows * 8, aux_bytes, S, DUAL);  // rows, then their labels
   double *aux = reinterpret_cast<double *>(smem + L.aux_off);
+  double *aux2 = reinterpret_cast<double *>(smem + L.aux2_off);        // w2 (DUAL)
   double *partial = reinterpret_cast<double *>(smem + L.partial_off);  // [TR][8]
+  double *partial2 = reinterpret_cast<double *>(smem + L.partial2_off);  // [TR][8] at w2 (DUAL)
   double *mult_s = reinterpret_cast<double *>(smem + L.mult_off);      // [TR]
   double *red = reinterpret_cast<double *>(smem + L.red_off);
   unsigned int *cnt = reinterpret_cast<unsigned int *>(smem + L.cnt_off);  // [S] warps done with the stage
@@ -159,8 +167,9 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     }
     mbar_init(wbar, 1);
     mbar_fence_init();
-    mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
+    mbar_expect_tx(wbar, (uint32_t)a.d * 8u * (DUAL ? 2u : 1u));
     tma_bulk_g2s(smem_u32(aux), a.w, (uint32_t)a.d * 8u, wbar);  // w: TMA-staged once per CTA
+    if (DUAL) tma_bulk_g2s(smem_u32(aux2), a.w2, (uint32_t)a.d * 8u, wbar);
     for (int s = 0; s < S; ++s) fill(s, s);
   }
   __syncthreads();
@@ -188,9 +197,11 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     const int sw = k & (NW - 1);  // this tile's scalar warp
     mbar_wait(bars + 8u * s, par);
     // labels ride in the stage: no warp ever waits on a global load inside the loop
+    const int srow = DUAL ? (lane & 15) : lane;   // the tile row this lane of the scalar warp evaluates
+    const bool sactive = warp == sw && srow < TR;
     double ylab = 0.0;
-    if (warp == sw && lane < TR)
-      ylab = *reinterpret_cast<const double *>(smem + (size_t)s * L.stage_stride + TR * row_bytes + lane * 8);
+    if (sactive)
+      ylab = *reinterpret_cast<const double *>(smem + (size_t)s * L.stage_stride + TR * row_bytes + srow * 8);
 
     double wreg[V][EPV];
 #pragma unroll
@@ -256,22 +267,42 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     }
     const double tot = warp_rows_reduce<R>(p, lane);
     if ((lane % (32 / R)) == 0) partial[(g * R + lane / (32 / R)) * 8 + wig] = tot;
+    if (DUAL) {  // the same retained tile against w2 (only the loss at w2 is wanted: no phase 2 for it)
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int vec = v * TPR + t;
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) wreg[v][e] = (vec < nvec) ? aux2[vec * EPV + e] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) sacc = fma(xd[r][v][e], wreg[v][e], sacc);
+        p[r] = sacc;
+      }
+      const double tot2 = warp_rows_reduce<R>(p, lane);
+      if ((lane % (32 / R)) == 0) partial2[(g * R + lane / (32 / R)) * 8 + wig] = tot2;
+    }
     __syncthreads();
 
     // scalar section: only the multiplier is needed by phase 2, so for logistic only the exp + reciprocal part of
     // the evaluation sits between the barriers; the log part follows, interleaved with this warp's phase-2 FMAs
     LogisticMid mid = {0.0, 0.0, 1.0, 1.0};
     bool row_ok = false;
-    if (warp == sw && lane < TR) {
+    if (sactive) {
+      const double *pp = (DUAL && lane >= 16) ? partial2 : partial;
       double pw[8];
 #pragma unroll
-      for (int wi = 0; wi < 8; ++wi) pw[wi] = (wi < WPG) ? partial[lane * 8 + wi] : 0.0;
+      for (int wi = 0; wi < 8; ++wi) pw[wi] = (wi < WPG) ? pp[srow * 8 + wi] : 0.0;
       const double m = ((pw[0] + pw[1]) + (pw[2] + pw[3])) + ((pw[4] + pw[5]) + (pw[6] + pw[7]));
-      row_ok = lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + lane);
+      row_ok = srow < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + srow);
       double mult, loss = 0.0;
       if (a.kind == AGD_GRAD_LOGISTIC) mult = logistic_head(m, ylab, mid);
       else loss_eval(a.kind, m, ylab, mult, loss);
-      mult_s[lane] = row_ok ? mult : 0.0;
+      if (!DUAL || lane < 16) mult_s[srow] = row_ok ? mult : 0.0;
       if (a.kind != AGD_GRAD_LOGISTIC) lossacc += row_ok ? loss : 0.0;
       cntacc += row_ok ? 1.0 : 0.0;
     }
@@ -338,17 +369,24 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       }
     }
   }
-  for (int off = 16; off >= 1; off >>= 1) {
+  // DUAL: lanes 16-31 hold the sums at w2.  Skipping the xor-16 step leaves the lane-0 total bit-identical to the
+  // single-point kernel's, whose lanes >= 16 only ever contribute exact zeros.
+  for (int off = DUAL ? 8 : 16; off >= 1; off >>= 1) {
     lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
     cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
   }
   if (lane == 0) { red[warp] = lossacc; red[8 + warp] = cntacc; }
+  if (DUAL && lane == 16) { red[16 + warp] = lossacc; red[24 + warp] = cntacc; }
   __syncthreads();
   if (tid == 0) {
-    double sacc = 0.0, cacc = 0.0;
+    double sacc = 0.0, cacc = 0.0, sacc2 = 0.0, cacc2 = 0.0;
     for (int wi = 0; wi < NW; ++wi) { sacc += red[wi]; cacc += red[8 + wi]; }
+    if (DUAL)
+      for (int wi = 0; wi < NW; ++wi) { sacc2 += red[16 + wi]; cacc2 += red[24 + wi]; }
     slab[a.d] = sacc;
     slab[a.d + 1] = cacc;
+    slab[a.d + 2] = sacc2;   // loss sum and row count at w2 (zero when the launch has no second point)
+    slab[a.d + 3] = cacc2;
   }
 }
 
@@ -476,7 +514,7 @@ k1_ws_kernel(const K1Args a, const int nvec, const long long ntiles, const uint3
       lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
       cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
     }
-    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; }
+    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; }
    }
     return;
   }
@@ -610,13 +648,16 @@ template <> __device__ __forceinline__ double load_elem<__nv_bfloat16>(const __n
 }
 
 // ---------------------------------------------------------------- generic shapes
+// a.w2 != nullptr: the loss (not the gradient) is also evaluated at w2 in the same sweep -- threads 32..32+R-1 play the
+// part of threads 0..R-1 for it, so its sum is formed exactly as a launch of its own would form it.
 template <typename T>
 __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const long long ntiles) {
   constexpr int R = 8;
-  __shared__ double part[R][8];
+  __shared__ double part[2][R][8];
   __shared__ double mult_s[R];
-  __shared__ double red[16];
+  __shared__ double red[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool dual = a.w2 != nullptr;
   const T *X = reinterpret_cast<const T *>(a.X);
   double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
   for (int c = tid; c <= a.d; c += 256) slab[c] = 0.0;
@@ -625,28 +666,46 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
     const long long row0 = tile * R;
     const long long left = a.rows - row0;
     const int rv = left < R ? (int)left : R;
-    double p[R];
+    double p[R], p2[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) p[r] = 0.0;
-    for (int c = tid; c < a.d; c += 256) {
-      const double wc = a.w[c];
+    for (int r = 0; r < R; ++r) { p[r] = 0.0; p2[r] = 0.0; }
+    if (!dual) {
+      for (int c = tid; c < a.d; c += 256) {
+        const double wc = a.w[c];
 #pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (r < rv) p[r] = fma(load_elem<T>(&X[(size_t)(row0 + r) * a.d + c]), wc, p[r]);
+        for (int r = 0; r < R; ++r)
+          if (r < rv) p[r] = fma(load_elem<T>(&X[(size_t)(row0 + r) * a.d + c]), wc, p[r]);
+      }
+    } else {
+      for (int c = tid; c < a.d; c += 256) {
+        const double wc = a.w[c], wc2 = a.w2[c];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r < rv) {
+            const double xv = load_elem<T>(&X[(size_t)(row0 + r) * a.d + c]);
+            p[r] = fma(xv, wc, p[r]);
+            p2[r] = fma(xv, wc2, p2[r]);
+          }
+      }
     }
     const double tot = warp_rows_reduce<R>(p, lane);
-    if ((lane & 3) == 0) part[lane >> 2][warp] = tot;
+    if ((lane & 3) == 0) part[0][lane >> 2][warp] = tot;
+    if (dual) {
+      const double tot2 = warp_rows_reduce<R>(p2, lane);
+      if ((lane & 3) == 0) part[1][lane >> 2][warp] = tot2;
+    }
     __syncthreads();
-    if (tid < R) {
+    const int which = tid >> 5, srow = tid & 31;
+    if (srow < R && (which == 0 || (dual && which == 1))) {
       double m = 0.0;
 #pragma unroll
-      for (int wi = 0; wi < 8; ++wi) m += part[tid][wi];
+      for (int wi = 0; wi < 8; ++wi) m += part[which][srow][wi];
       double mult = 0.0, loss = 0.0;
-      if (tid < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + tid)) {
-        loss_eval(a.kind, m, a.labels[row0 + tid], mult, loss);
+      if (srow < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + row0 + srow)) {
+        loss_eval(a.kind, m, a.labels[row0 + srow], mult, loss);
         cntacc += 1.0;
       }
-      mult_s[tid] = mult;
+      if (which == 0) mult_s[srow] = mult;
       lossacc += loss;
     }
     __syncthreads();
@@ -665,15 +724,23 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
   if (lane == 0) { red[warp] = lossacc; red[8 + warp] = cntacc; }
   __syncthreads();
   if (tid == 0) {
-    double sacc = 0.0, cacc = 0.0;
-    for (int wi = 0; wi < 8; ++wi) { sacc += red[wi]; cacc += red[8 + wi]; }
+    // warp 0 carries the sums at w, warp 1 those at w2 (all other entries are exact zeros)
+    double sacc = 0.0, cacc = 0.0, sacc2 = 0.0, cacc2 = 0.0;
+    for (int wi = 0; wi < 8; ++wi) {
+      if (dual && wi == 1) { sacc2 = red[wi]; cacc2 = red[8 + wi]; continue; }
+      sacc += red[wi];
+      cacc += red[8 + wi];
+    }
     slab[a.d] = sacc;
     slab[a.d + 1] = cacc;
+    slab[a.d + 2] = sacc2;
+    slab[a.d + 3] = cacc2;
   }
 }
 
 // ---------------------------------------------------------------- slab reduction (combOp, AGD.scala:201-204)
-// out[c] = sum over slabs of column c, c <= d + 1 (gradient, loss sum, row count).  32 columns per block; 8 slab groups per block sum
+// out[c] = sum over slabs of column c, c <= d + 3 (gradient, loss sum, row count, then the same pair at the second point of a
+// fused sweep).  32 columns per block; 8 slab groups per block sum
 // strided subsets (slab b -> group b % 8) with 4 loads in flight, then group 0 adds the 8 group sums in
 // order: the summation tree is fixed, so the result is bit-reproducible.
 template <bool PUB>
@@ -683,9 +750,9 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
   __shared__ bool last;
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  const size_t stride = (size_t)d + 2;
+  const size_t stride = (size_t)d + 4;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  if (c <= d + 1) {
+  if (c <= d + 3) {
     int b = grp;
     for (; b + 24 < blocks; b += 32) {
       const double v0 = slabs[(size_t)b * stride + c], v1 = slabs[(size_t)(b + 8) * stride + c],
@@ -696,7 +763,7 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
   }
   part[grp][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  if (grp == 0 && c <= d + 1) {
+  if (grp == 0 && c <= d + 3) {
     double t = 0.0;
 #pragma unroll
     for (int gi = 0; gi < 8; ++gi) t += part[gi][cl];
@@ -749,7 +816,7 @@ inline bool ring_shape(int32_t d, int elem_bytes, RingShape &sh, int &nvec) {
   return false;
 }
 
-template <typename T, int NT, int TPR, int V, int R, int MINB>
+template <typename T, int NT, int TPR, int V, int R, int MINB, bool DUAL = false>
 cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
   constexpr int EPV = Elem<T>::EPV;
   constexpr int NG = NT / TPR;
@@ -764,10 +831,10 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
   }
   const uint32_t budget = (227u * 1024u - MINB * 1024u) / MINB;
   int stages = a.stages > 0 ? a.stages : 4;
-  while (stages > 1 && ring_layout(tile_bytes, aux_bytes, stages).total > budget) --stages;
+  while (stages > 1 && ring_layout(tile_bytes, aux_bytes, stages, DUAL).total > budget) --stages;
   a.stages = stages;
-  const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages);
-  auto kern = k1_ring_kernel<T, NT, TPR, V, R, MINB>;
+  const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages, DUAL);
+  auto kern = k1_ring_kernel<T, NT, TPR, V, R, MINB, DUAL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) return e;
   const long long ntiles = (a.rows + TR - 1) / TR;
@@ -782,6 +849,15 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
 cudaError_t launch_ring_bf16(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
                              cudaStream_t st) {
   using T = __nv_bfloat16;
+  if (a.w2) {  // fused sweep: tiles of at most 16 rows
+    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 2, 2, true>(a, nvec, sm_count, blocks_out, st);
+    switch (sh.tpr) {
+      case 64: return launch_ring_inst<T, 256, 64, 1, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
+      case 128: return launch_ring_inst<T, 256, 128, 1, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
+      case 256: return launch_ring_inst<T, 256, 256, 1, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 2, 2>(a, nvec, sm_count, blocks_out, st);
   switch (sh.tpr) {
     case 32: return launch_ring_inst<T, 256, 32, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
@@ -794,6 +870,13 @@ cudaError_t launch_ring_bf16(const K1Args &a, const RingShape &sh, int nvec, int
 template <typename T>
 cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
                           cudaStream_t st) {
+  if (a.w2) {  // fused sweep: tiles of at most 16 rows
+    if (sh.v == 4) return launch_ring_inst<T, 256, 256, 4, 2, 2, true>(a, nvec, sm_count, blocks_out, st);
+    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
+    if (sh.tpr == 128) return launch_ring_inst<T, 256, 128, 1, 8, 2, true>(a, nvec, sm_count, blocks_out, st);
+    if (sh.tpr == 256) return launch_ring_inst<T, 256, 256, 1, 8, 2, true>(a, nvec, sm_count, blocks_out, st);
+    return cudaErrorInvalidValue;
+  }
   if (sh.v == 1) {
     switch (sh.tpr) {
       case 32: return launch_ring_inst<T, 256, 32, 1, 4, 2>(a, nvec, sm_count, blocks_out, st);
@@ -870,6 +953,14 @@ int k1_ring_supported(int32_t d, int elem_bytes) {
   return ring_shape(d, elem_bytes, sh, nvec) ? 1 : 0;
 }
 
+// the fused (two-point) sweep exists for ring shapes whose tile has at most 16 rows
+int k1_ring_dual_supported(int32_t d, int elem_bytes) {
+  RingShape sh;
+  int nvec;
+  if (!ring_shape(d, elem_bytes, sh, nvec)) return 0;
+  return (256 / sh.tpr) * sh.r <= 16 ? 1 : 0;
+}
+
 cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
   RingShape sh;
   int nvec = 0;
@@ -883,7 +974,7 @@ cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *b
 cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
   RingShape sh;
   int nvec = 0;
-  if (elem_bytes == 2 || !ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
+  if (elem_bytes == 2 || a.w2 || !ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
   if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
   if (elem_bytes == 4) return launch_ws_t<float>(a, sh, nvec, sm_count, blocks_out, st);
   return launch_ws_t<double>(a, sh, nvec, sm_count, blocks_out, st);
@@ -907,7 +998,7 @@ cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int
 cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, const XchgPub *pub,
                              cudaStream_t st) {
   (void)rows;
-  const int grid = (d + 2 + 31) / 32;
+  const int grid = (d + 4 + 31) / 32;
   if (pub) k1_reduce_kernel<true><<<grid, 256, 0, st>>>(slabs, blocks, d, out, *pub);
   else k1_reduce_kernel<false><<<grid, 256, 0, st>>>(slabs, blocks, d, out, XchgPub());
   return cudaGetLastError();

@@ -253,7 +253,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
       lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
       cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
     }
-    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; }
+    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; }
    }
   } else if (warp >= 20) {
     // ===================== flush warpgroup: owns the fp64 gradient, drains TMEM every kFlush tiles ==========

@@ -261,6 +261,19 @@ class DeviceDataset:
         N.check(N.lib().agd_smooth(self.h, _grad_kind(gradient), _ptr(w), C.byref(loss), _ptr(g), C.byref(cnt)), self.h)
         return loss.value, g, cnt.value
 
+    def smooth_pair(self, gradient: Gradient, w, w2):
+        """applySmooth at w plus the loss at w2 from ONE sweep over the shards (the fused form of AGD.scala:250 + :304):
+        (loss/count, grad/count, count, loss2/count)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        w2 = np.ascontiguousarray(w2, dtype=np.float64)
+        if w.shape[0] != self.d or w2.shape[0] != self.d:
+            raise ValueError("weights have the wrong dimension")
+        g = np.empty(self.d, dtype=np.float64)
+        loss, loss2, cnt = C.c_double(), C.c_double(), C.c_int64()
+        N.check(N.lib().agd_smooth_pair(self.h, _grad_kind(gradient), _ptr(w), _ptr(w2), C.byref(loss), _ptr(g),
+                                        C.byref(cnt), C.byref(loss2)), self.h)
+        return loss.value, g, cnt.value, loss2.value
+
     def prox(self, updater: Updater, w, g, step: float, reg: float):
         """applyProjector (AGD.scala:214-222): (regVal, newWeights)."""
         w = np.ascontiguousarray(w, dtype=np.float64)
@@ -337,12 +350,15 @@ class RunStats:
     device_ms_total: float
     collective_calls: int
     collective_kind: int = 0
+    fused_passes: int = 0      # evaluations that shared a sweep over X with another one (sweeps = passes - fused_passes)
+    wasted_passes: int = 0
 
 
 def _stats(st: N.Stats) -> RunStats:
     return RunStats(st.iterations, st.passes, st.backtracks, st.restarts, bool(st.converged), bool(st.stopped_nan),
                     bool(st.nonterminating), st.final_L, st.final_theta, st.seconds_total, st.k1_ms_total,
-                    st.k1_launches, st.gpu_launches, st.allreduce_ms_total, st.device_ms_total, st.collective_calls, st.collective_kind)
+                    st.k1_launches, st.gpu_launches, st.allreduce_ms_total, st.device_ms_total, st.collective_calls, st.collective_kind,
+                    st.fused_passes, st.wasted_passes)
 
 
 # --------------------------------------------------------------------------- the optimizer
@@ -361,6 +377,7 @@ class AcceleratedGradientDescent:
         self.alpha = 0.9                    # :50
         self.mayRestart = True              # :51
         self.memoize = False                # extension: AGD_FLAG_MEMOIZE_FX (bit-identical, fewer passes)
+        self.fuse = True                    # pass fusion (AGD_FLAG_NO_FUSE clears it): same evaluations, fewer sweeps
         self.last_stats: Optional[RunStats] = None
 
     def setConvergenceTol(self, tol: float): self.convergenceTol = tol; return self       # :57
@@ -374,11 +391,12 @@ class AcceleratedGradientDescent:
     def setGradient(self, gradient: Gradient): self.gradient = gradient; return self      # :106
     def setUpdater(self, updater: Updater): self.updater = updater; return self           # :117
     def setMemoize(self, on: bool): self.memoize = on; return self
+    def setFuse(self, on: bool): self.fuse = on; return self
 
     def optimize(self, data: DeviceDataset, initialWeights) -> np.ndarray:                # :128-143
         w, _, st = run_with_stats(data, self.gradient, self.updater, self.convergenceTol, self.numIterations,
                                   self.regParam, initialWeights, self.L0, self.Lexact, self.beta, self.alpha,
-                                  self.mayRestart, memoize=self.memoize)
+                                  self.mayRestart, memoize=self.memoize, fuse=self.fuse)
         self.last_stats = st
         return w
 
@@ -393,14 +411,14 @@ class AcceleratedGradientDescent:
 
 
 def run_with_stats(data: DeviceDataset, gradient, updater, convergenceTol, numIterations, regParam, initialWeights,
-                   L0=1.0, Lexact=float("inf"), beta=0.5, alpha=0.9, mayRestart=True, memoize=False):
+                   L0=1.0, Lexact=float("inf"), beta=0.5, alpha=0.9, mayRestart=True, memoize=False, fuse=True):
     if not isinstance(data, DeviceDataset):
         raise TypeError("data must be a DeviceDataset (Context.parallelize(...)); there is no CPU path")
     w0 = np.ascontiguousarray(initialWeights, dtype=np.float64)
     if w0.ndim != 1 or w0.shape[0] != data.d:
         raise ValueError(f"initialWeights has size {w0.shape}, data has {data.d} features")
     p = N.Params(convergenceTol, int(numIterations), regParam, L0, Lexact, beta, alpha, int(bool(mayRestart)),
-                 _grad_kind(gradient), _upd_kind(updater), N.FLAG_MEMOIZE_FX if memoize else 0)
+                 _grad_kind(gradient), _upd_kind(updater), (N.FLAG_MEMOIZE_FX if memoize else 0) | (0 if fuse else N.FLAG_NO_FUSE))
     w = np.empty_like(w0)
     hist = np.empty(max(int(numIterations), 1), dtype=np.float64)
     nh, st = C.c_int32(), N.Stats()

@@ -404,6 +404,96 @@ def test_suite_T5_wide_rows(agd, ctx, oracle):                                  
     data.close()
 
 
+
+# ------------------------------------------------------------------ pass fusion: two points, one sweep
+PAIR_SHAPES = [((3001, 1024), "f32", "auto"), ((2000, 512), "f32", "auto"), ((501, 1001), "f32", "auto"),
+               ((777, 2048), "f32", "auto"), ((300, 4096), "f32", "auto"), ((1500, 512), "f64", "auto"),
+               ((400, 2048), "f64", "auto"), ((10, 20000), "f32", "auto"), ((700, 300), "f64", "generic"),
+               ((2000, 1024), "bf16", "ring"), ((900, 2048), "bf16", "ring"), ((600, 4096), "bf16", "ring")]
+
+
+@pytest.mark.parametrize("grad", GRADS)
+@pytest.mark.parametrize("shape,store,variant", PAIR_SHAPES)
+def test_smooth_pair_equals_two_sweeps_bit_for_bit(agd, ctx, grad, shape, store, variant):
+    """agd_smooth_pair (applySmooth at w + the loss at w2 from one read of X) returns exactly the bits of two agd_smooth calls."""
+    n, d = shape
+    rng = np.random.default_rng(77 + n + d)
+    X, y = make_data(rng, n, d, grad, np.float64 if store == "f64" else np.float32)
+    w = rng.standard_normal(d) * 0.7 / np.sqrt(d)
+    w2 = w + rng.standard_normal(d) * 0.2 / np.sqrt(d)
+    ds = ctx.parallelize(y, X, store=store)
+    ds.set_option("k1_variant", variant)
+    a = ds.smooth(G(agd, grad), w)
+    b = ds.smooth(G(agd, grad), w2)
+    loss, g, cnt, loss2 = ds.smooth_pair(G(agd, grad), w, w2)
+    assert cnt == a[2] == n
+    assert loss == a[0] and np.array_equal(g, a[1])
+    assert loss2 == b[0]
+    ds.close()
+
+
+def test_smooth_pair_csr_and_unsupported_kernels(agd, ctx, oracle):
+    rng = np.random.default_rng(5)
+    n, d, k = 3000, 5000, 24
+    idx = np.sort(np.stack([rng.choice(d, k, replace=False) for _ in range(n)]), axis=1).astype(np.int32)
+    val = rng.standard_normal((n, k)).astype(np.float32)
+    rowptr = np.arange(n + 1, dtype=np.int64) * k
+    y = (rng.random(n) > 0.5).astype(np.float64)
+    w, w2 = rng.standard_normal(d) * 0.1, rng.standard_normal(d) * 0.1
+    ds = ctx.parallelize_csr(y, rowptr, idx.ravel(), val.ravel(), d, store="f32")
+    a, b = ds.smooth(agd.HingeGradient(), w), ds.smooth(agd.HingeGradient(), w2)
+    loss, g, cnt, loss2 = ds.smooth_pair(agd.HingeGradient(), w, w2)
+    assert cnt == n
+    np.testing.assert_allclose(loss, a[0], rtol=1e-13)          # CSR sums are atomics: equal to rounding only
+    np.testing.assert_allclose(loss2, b[0], rtol=1e-13)
+    assert rel_err(g, a[1]) < 1e-13
+    ds.close()
+    # kernels without a two-point form refuse (agd_run then simply does not fuse)
+    X = rng.standard_normal((300, 1024)).astype(np.float32)
+    yd = (rng.random(300) > 0.5).astype(np.float64)
+    ds = ctx.parallelize(yd, X, store="bf16")                   # tcgen05 path
+    with pytest.raises(agd.NativeError, match="two-point"):
+        ds.smooth_pair(agd.LogisticGradient(), np.zeros(1024), np.zeros(1024))
+    ds.close()
+    ds = ctx.parallelize(yd[:100], X[:100, :36].copy(), store="f32")   # 32-row tiles
+    with pytest.raises(agd.NativeError, match="two-point"):
+        ds.smooth_pair(agd.LogisticGradient(), np.zeros(36), np.zeros(36))
+    w_, h_, st = agd.run_with_stats(ds, agd.LogisticGradient(), agd.SimpleUpdater(), 0.0, 5, 0.0, np.zeros(36))
+    assert st.fused_passes == 0 and st.k1_launches == st.passes + st.wasted_passes
+    ds.close()
+
+
+FUSE_CASES = [(20000, 1024, "logistic", "simple", 0.0, "f32", 12, {}),
+              (6000, 1001, "logistic", "l1", 0.002, "f32", 12, {}),
+              (5000, 512, "hinge", "squared_l2", 0.1, "f32", 15, {}),
+              (4000, 2048, "least_squares", "simple", 0.0, "f64", 25, {"L0": 1e-3}),          # L-increase branch
+              (4000, 300, "logistic", "simple", 0.0, "f64", 20, {"beta": 1.0, "L0": 0.25, "Lexact": 0.25, "may_restart": False}),
+              (3000, 20000, "logistic", "squared_l2", 0.01, "f32", 8, {}),                    # generic kernel
+              (1000, 512, "least_squares", "simple", 0.0, "f64", 60, {"tol": 1e-6})]          # leaves through :322-324
+
+
+@pytest.mark.parametrize("case", FUSE_CASES, ids=[f"{c[0]}x{c[1]}-{c[2]}-{c[3]}-{i}" for i, c in enumerate(FUSE_CASES)])
+def test_fused_run_is_bit_identical_to_unfused(agd, ctx, case):
+    """Default agd_run lets applySmooth(x) of AGD.scala:304 ride along with the next iteration's applySmooth(y) (:250):
+    same evaluations, same weights and loss history bit for bit, one sweep over X fewer per iteration."""
+    n, d, grad, upd, reg, store, iters, kw = case
+    rng = np.random.default_rng(n + d + iters + 9)
+    X, y = make_data(rng, n, d, grad, np.float32 if store == "f32" else np.float64)
+    data = ctx.parallelize(y, X, store=store)
+    args = (data, G(agd, grad), U(agd, upd), kw.get("tol", 0.0), iters, reg, np.zeros(d), kw.get("L0", 1.0),
+            kw.get("Lexact", float("inf")), kw.get("beta", 0.5), kw.get("alpha", 0.9), kw.get("may_restart", True))
+    w1, h1, s1 = agd.run_with_stats(*args, fuse=True)
+    w0, h0, s0 = agd.run_with_stats(*args, fuse=False)
+    assert np.array_equal(w1, w0) and np.array_equal(h1, h0)
+    assert (s1.iterations, s1.passes, s1.backtracks, s1.restarts, s1.converged) == \
+           (s0.iterations, s0.passes, s0.backtracks, s0.restarts, s0.converged)
+    assert s0.fused_passes == 0 and s0.k1_launches == s0.passes + s0.wasted_passes
+    assert s1.fused_passes == s1.iterations - 1            # every history evaluation but the last shared a sweep
+    assert s1.k1_launches == s1.passes + s1.wasted_passes - s1.fused_passes
+    wm, hm, sm = agd.run_with_stats(*args, memoize=True)   # memoisation leaves nothing to fuse unless x moved
+    assert np.array_equal(wm, w0) and np.array_equal(hm, h0)
+    data.close()
+
 # ------------------------------------------------------------------ whole-loop parity (agd_run)
 CASES = [
     # (n, d, grad, upd, reg, store, iters, kwargs)
