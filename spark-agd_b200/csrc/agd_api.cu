@@ -120,7 +120,7 @@ struct agd_handle {
   bool comm_ready = false;
   int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised, 4 tcgen05 (bf16)
   int ring_stages = 0;
-  int tune_rows = 0, tune_ctas = 0;
+  int tune_rows = 0, tune_ctas = 0, tune_full = 0;
   int k1_diag = 0;
   unsigned long long sample_seed = 0, sample_thresh = 0;  // mini-batch row mask of the current pass (0 = every row)
   int collective = 0;        // 0 = auto (peer memory if every pair of ranks can map each other, else NCCL), 1 = nccl, 2 = p2p
@@ -481,7 +481,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     K1Args a;
     a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.w2 = w2_of ? w2_of(D) : nullptr; a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
     a.stages = h->ring_stages; a.slab_stride = d + 4;
-    a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas;
+    a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas; a.tune_full = h->tune_full;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     bool ring = k1_ring_supported(d, eb) != 0;
     if (h->k1_variant == 2) ring = false;
@@ -1025,6 +1025,7 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
   if (!strcmp(key, "k1_diag")) { h->k1_diag = atoi(value); return 0; }
   if (!strcmp(key, "ring_rows")) { h->tune_rows = atoi(value); return 0; }
   if (!strcmp(key, "ring_ctas")) { h->tune_ctas = atoi(value); return 0; }
+  if (!strcmp(key, "ring_predicated")) { h->tune_full = atoi(value); return 0; }
   return fail(h, "unknown option %s", key);
 }
 

@@ -24,6 +24,7 @@ struct K1Args {
   long long row_base;     // global index of the shard's first row
   int32_t tune_rows;      // 0 = default; rows per tile of the headline ring shape (4|8)
   int32_t tune_ctas;      // 0 = default; resident CTAs per SM (1|2|3)
+  int32_t tune_full;      // 0 = default; 1 = keep the column predicates even when every thread owns whole vectors
 };
 
 // launch helpers (k1_dense.cu); return the number of blocks that wrote a slab

@@ -8,8 +8,9 @@
 // (the driver loop branches on catastrophically cancelling fp64 quantities, AGD.scala:273-281,327).
 //
 // k1_ring_kernel (hot path, d*sizeof(T) a multiple of 16 and d <= 1024 vectors/row):
-//   * one producer lane streams 32 KB row tiles HBM -> shared memory with TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx) through an S-stage full/empty ring, labels ride along;
+//   * 32 KB row tiles stream HBM -> shared memory with TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx) through an S-stage ring, labels ride along; a stage is refilled right behind the
+//     CTA barrier that follows its last read;
 //   * w is staged once per CTA with the same TMA path, then lives in registers;
 //   * 256 consumer threads: thread t of a row group owns 128-bit column vectors {t, t+TPR, ...};
 //     it pulls its R x V vectors of the tile out of shared memory (LDS.128), converts once to fp64,
@@ -130,6 +131,9 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
   static_assert(TR <= kMaxTileRows && TR % 2 == 0 && (NW & (NW - 1)) == 0, "tile rows / warps");
   // DUAL: lanes 0-15 of the scalar warp evaluate the rows at w, lanes 16-31 the same rows at w2
   static_assert(!DUAL || TR <= 16, "pass fusion needs the tile's rows twice in one warp");
+  // two accumulator sets (even / odd rows) halve the DFMA dependency chains; with V * EPV > 4 columns per thread there are
+  // enough independent chains already
+  constexpr bool kSplitAcc = R > 1 && V * EPV <= 4;
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int S = a.stages;
@@ -175,6 +179,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
   __syncthreads();
 
   const int g = tid / TPR, t = tid % TPR, wig = t >> 5;
+  const bool full_row = nvec == V * TPR && a.tune_full == 0;
   double acc[V][EPV], acc2[V][EPV];
   mbar_wait(wbar, 0);  // w is in shared memory; it is re-read per tile so that it is not live across phase 2
 #pragma unroll
@@ -185,6 +190,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       acc2[v][e] = 0.0;
     }
   double lossacc = 0.0, cntacc = 0.0;
+  const int rv_last = (int)(a.rows - (ntiles - 1) * TR);
 
   int k = 0, s = -1;
   uint32_t par = 1;
@@ -192,8 +198,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     if (++s == S) s = 0;          // ring slot and its mbarrier phase, kept incrementally
     if (s == 0) par ^= 1u;
     const long long row0 = tile * TR;
-    const long long left = a.rows - row0;
-    const int rv = left < TR ? (int)left : TR;
+    const int rv = (tile == ntiles - 1) ? rv_last : TR;  // only the shard's last tile can be ragged
     const int sw = k & (NW - 1);  // this tile's scalar warp
     mbar_wait(bars + 8u * s, par);
     // labels ride in the stage: no warp ever waits on a global load inside the loop
@@ -204,23 +209,37 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       ylab = *reinterpret_cast<const double *>(smem + (size_t)s * L.stage_stride + TR * row_bytes + srow * 8);
 
     double wreg[V][EPV];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int vec = v * TPR + t;
-#pragma unroll
-      for (int e = 0; e < EPV; ++e) wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
-    }
     // pull this thread's R x V vectors out of the stage and widen them to fp64 once
     double xd[R][V][EPV];
     const unsigned char *stage = smem + (size_t)s * L.stage_stride;
+    if (full_row) {  // every thread owns V whole vectors of the row (d = 1024 fp32 ...): no predicates, no zero fill
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+      for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) wreg[v][e] = aux[(v * TPR + t) * EPV + e];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const uint4 raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)(v * TPR + t) * 16);
+          cvt_vec<T, EPV>(raw, xd[r][v]);
+        }
+    } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const int vec = v * TPR + t;
-        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-        if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)vec * 16);
-        cvt_vec<T, EPV>(raw, xd[r][v]);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int vec = v * TPR + t;
+          uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+          if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)vec * 16);
+          cvt_vec<T, EPV>(raw, xd[r][v]);
+        }
       }
     }
     if (rv < TR) {  // ragged last tile: rows past the shard hold stale bytes
@@ -233,16 +252,15 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
             for (int e = 0; e < EPV; ++e) xd[r][v][e] = 0.0;
         }
     }
-    __syncwarp();
-    if (lane == 0) {  // the last warp to leave the stage refills it (no dedicated producer warp)
-      const unsigned int done = atomicAdd(&cnt[s], 1u);
-      if (done == NW - 1) {
-        cnt[s] = 0u;
-        fill((long long)k + S, s);
-      }
-    }
-
     if (a.kind == 100 || a.kind == 101) {  // diagnostics (option k1_diag): 100 = stream + widen only, 101 = + phase 1, no barriers
+      __syncwarp();
+      if (lane == 0) {  // no CTA barrier in these modes: the last warp to leave the stage refills it
+        const unsigned int done = atomicAdd(&cnt[s], 1u);
+        if (done == NW - 1) {
+          cnt[s] = 0u;
+          fill((long long)k + S, s);
+        }
+      }
       double sacc = 0.0;
 #pragma unroll
       for (int r = 0; r < R; ++r)
@@ -287,6 +305,9 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       if ((lane % (32 / R)) == 0) partial2[(g * R + lane / (32 / R)) * 8 + wig] = tot2;
     }
     __syncthreads();
+    // every warp holds its part of the tile in registers: the stage is free.  One lane of a warp that is not this tile's
+    // scalar warp re-arms the mbarrier and issues the TMA refill (no producer warp, no counters).
+    if (warp == ((sw + NW / 2) & (NW - 1)) && lane == 0) fill((long long)k + S, s);
 
     // scalar section: only the multiplier is needed by phase 2, so for logistic only the exp + reciprocal part of
     // the evaluation sits between the barriers; the log part follows, interleaved with this warp's phase-2 FMAs
@@ -319,7 +340,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
         for (int v = 0; v < V; ++v)
 #pragma unroll
           for (int e = 0; e < EPV; ++e) {
-            if (R > 1 && (r & 1)) acc2[v][e] = fma(mu[r], xd[r][v][e], acc2[v][e]);
+            if (kSplitAcc && (r & 1)) acc2[v][e] = fma(mu[r], xd[r][v][e], acc2[v][e]);
             else acc[v][e] = fma(mu[r], xd[r][v][e], acc[v][e]);
           }
       }
@@ -891,6 +912,7 @@ cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm
           case 43: return launch_ring_inst<T, 256, 256, 1, 4, 3>(a, nvec, sm_count, blocks_out, st);
           case 44: return launch_ring_inst<T, 128, 128, 2, 4, 4>(a, nvec, sm_count, blocks_out, st);  // 128-thread CTAs
           case 45: return launch_ring_inst<T, 128, 128, 2, 4, 3>(a, nvec, sm_count, blocks_out, st);
+          case 46: return launch_ring_inst<T, 256, 128, 2, 4, 2>(a, nvec, sm_count, blocks_out, st);  // 2 row groups x 2 vectors
           default: return launch_ring_inst<T, 256, 256, 1, 8, 2>(a, nvec, sm_count, blocks_out, st);
         }
       }
