@@ -194,16 +194,18 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
 
   int k = 0, s = -1;
   uint32_t par = 1;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+  const int ntiles32 = (int)ntiles, last_tile = ntiles32 - 1, tile_step = (int)gridDim.x;  // the launch keeps ntiles < 2^31
+  for (int tile = blockIdx.x; tile < ntiles32; tile += tile_step, ++k) {
     if (++s == S) s = 0;          // ring slot and its mbarrier phase, kept incrementally
     if (s == 0) par ^= 1u;
-    const long long row0 = tile * TR;
-    const int rv = (tile == ntiles - 1) ? rv_last : TR;  // only the shard's last tile can be ragged
+    const int rv = (tile == last_tile) ? rv_last : TR;  // only the shard's last tile can be ragged
     const int sw = k & (NW - 1);  // this tile's scalar warp
     mbar_wait(bars + 8u * s, par);
     // labels ride in the stage: no warp ever waits on a global load inside the loop
     const int srow = DUAL ? (lane & 15) : lane;   // the tile row this lane of the scalar warp evaluates
-    const bool sactive = warp == sw && srow < TR;
+    // every lane of the scalar warp runs the evaluation (the label / partial-dot arrays have kMaxTileRows entries, lanes
+    // without a row read stale values and are masked by row_ok), so nothing needs initialising on the other warps
+    const bool sactive = warp == sw;
     double ylab = 0.0;
     if (sactive)
       ylab = *reinterpret_cast<const double *>(smem + (size_t)s * L.stage_stride + TR * row_bytes + srow * 8);
@@ -290,7 +292,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       for (int v = 0; v < V; ++v) {
         const int vec = v * TPR + t;
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) wreg[v][e] = (vec < nvec) ? aux2[vec * EPV + e] : 0.0;
+        for (int e = 0; e < EPV; ++e) wreg[v][e] = (full_row || vec < nvec) ? aux2[vec * EPV + e] : 0.0;
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -311,9 +313,10 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
 
     // scalar section: only the multiplier is needed by phase 2, so for logistic only the exp + reciprocal part of
     // the evaluation sits between the barriers; the log part follows, interleaved with this warp's phase-2 FMAs
-    LogisticMid mid = {0.0, 0.0, 1.0, 1.0};
+    LogisticMid mid;   // written and read by the scalar warp only
     bool row_ok = false;
     if (sactive) {
+      const long long row0 = (long long)tile * TR;
       const double *pp = (DUAL && lane >= 16) ? partial2 : partial;
       double pw[8];
 #pragma unroll
@@ -323,7 +326,7 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       double mult, loss = 0.0;
       if (a.kind == AGD_GRAD_LOGISTIC) mult = logistic_head(m, ylab, mid);
       else loss_eval(a.kind, m, ylab, mult, loss);
-      if (!DUAL || lane < 16) mult_s[srow] = row_ok ? mult : 0.0;
+      if (DUAL ? lane < 16 : srow < TR) mult_s[srow] = row_ok ? mult : 0.0;
       if (a.kind != AGD_GRAD_LOGISTIC) lossacc += row_ok ? loss : 0.0;
       cntacc += row_ok ? 1.0 : 0.0;
     }
