@@ -29,9 +29,10 @@ namespace agd {
 namespace {
 
 constexpr int kKR = 16;            // rows per tile = K of one MMA
-constexpr int kConsumers = 512;             // warpgroups 0-3
-constexpr int kThreads = kConsumers + 256;  // + warpgroup 4 (producer, MMA issuer, scalar, idle) + warpgroup 5 (flush)
-constexpr int kRegsConsumer = 64, kRegsAux = 56, kRegsFlush = 112;  // setmaxnreg: 80 at launch (768 threads)
+// RPT = rows per consumer thread.  RPT = 2: 512 consumers (+ 256 aux/flush threads, setmaxnreg 64/56/112 out of the 80 at
+// launch).  RPT = 4: 256 consumers, each w value fetched from shared memory serves four rows instead of two -- the kernel is
+// bound by shared-memory bandwidth (TMA writes + MMA operand reads + x reads + w reads), and w is the largest reader.
+constexpr int kRegsConsumer = 64, kRegsAux = 56, kRegsFlush = 112;
 constexpr int kFlush = 8;          // tiles between TMEM -> fp64 flushes (128 rows of fp32 accumulation)
 constexpr int kBlockBytes = kKR * 128;     // one [16 rows][64 features] swizzled block
 
@@ -72,6 +73,11 @@ __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap *map
                "l"(map), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -85,7 +91,7 @@ __host__ __device__ inline TcLayout tc_layout(int ring_groups, int group_bytes, 
   L.w_off = (uint32_t)ring_groups * group_bytes;
   L.b2_off = L.w_off + (uint32_t)d * 8;
   L.partial_off = L.b2_off + 2 * 512;
-  L.bars_off = L.partial_off + 2 * kKR * 2 * 8;
+  L.bars_off = L.partial_off + 2 * kKR * 16 * 8;
   L.tmem_off = L.bars_off + (2 * (uint32_t)ring_groups + 8) * 8;
   L.total = L.tmem_off + 16;
   return L;
@@ -103,16 +109,27 @@ struct TcArgs {
   int ngt;          // groups per tile = d / (64 * gb)
   int ring_groups;  // ring capacity in groups
   int tmem_cols;    // power of two >= max(32, d / 8)
+  int one_copy;     // 1: a ring group arrives as ONE 3-D TMA copy [gb blocks][16 rows][64 features] instead of gb 2-D copies
+  int diag;         // option k1_diag: 100 = consumers skip the arithmetic, 101 = the MMAs are not issued (timing bisection only)
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
-k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const long long ntiles) {
+// RPT = 0 selects the row-per-lane consumer mapping: a warp covers all 16 rows of the tile for two adjacent 8-feature chunks,
+// so its w reads are broadcasts (one shared-memory wavefront instead of four) and each lane owns one row's partial dot.
+__host__ __device__ constexpr int tc_consumers(int rpt) { return rpt == 4 ? 256 : 512; }
+template <int RPT>
+__global__ void __launch_bounds__(tc_consumers(RPT) + 256, 1)
+k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap3, const TcArgs a,
+             const long long ntiles) {
+  constexpr int kConsumers = tc_consumers(RPT);   // RPT > 0: 64 threads (one 16-byte vector each) per group row
+  constexpr int kThreads = kConsumers + 256;   // + warpgroup (producer, MMA issuer, scalar, idle) + flush warpgroup
+  constexpr int kCW = kConsumers / 32;         // consumer warps; the aux warps follow
+  constexpr bool kRepartition = RPT != 4;      // 768 threads start with 80 registers: move some to the flush warpgroup
   extern __shared__ __align__(1024) unsigned char smem[];
   const int group_bytes = a.gb * kBlockBytes;
   const TcLayout L = tc_layout(a.ring_groups, group_bytes, a.d);
   double *w_s = reinterpret_cast<double *>(smem + L.w_off);
   unsigned char *b2 = smem + L.b2_off;                                       // [2][512 B]
-  double *partial = reinterpret_cast<double *>(smem + L.partial_off);         // [2][16 rows][2]
+  double *partial = reinterpret_cast<double *>(smem + L.partial_off);         // [2][16 rows][2] (RPT > 0) or [2][16 rows][16 warps]
   const uint32_t bars = smem_u32(smem + L.bars_off);
   const int RG = a.ring_groups;
   // full[g] = bars + 8g ; empty[g] = bars + 8(RG+g) ; then wbar, b2_full[2], b2_empty[2], tile_done, flush_done
@@ -148,9 +165,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 16 && warp < 20) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
-   if (warp == 16) {
+  if (warp >= kCW && warp < kCW + 4) {
+   if (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsAux));
+   if (warp == kCW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
@@ -165,12 +182,16 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
           if (wrapped) mbar_wait(bars + 8u * (RG + slot), epar);
           const uint32_t full = bars + 8u * slot;
           mbar_expect_tx(full, (uint32_t)group_bytes);  // rows past the shard are zero-filled by TMA
-          for (int b = 0; b < a.gb; ++b)
-            tma_tile_2d(smem_u32(smem + (size_t)slot * group_bytes + b * kBlockBytes), &tmap, (gi * a.gb + b) * 64, (int)row0, full);
+          if (a.one_copy) {
+            tma_tile_3d(smem_u32(smem + (size_t)slot * group_bytes), &tmap3, 0, (int)row0, gi * a.gb, full);
+          } else {
+            for (int b = 0; b < a.gb; ++b)
+              tma_tile_2d(smem_u32(smem + (size_t)slot * group_bytes + b * kBlockBytes), &tmap, (gi * a.gb + b) * 64, (int)row0, full);
+          }
         }
       }
     }
-   } else if (warp == 17) {
+   } else if (warp == kCW + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instr desc: D=F32, A=B=BF16, A MN-major, B K-major, N=16, M=128
@@ -193,6 +214,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
                                    ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
             const uint32_t taddr = tmem_base + (uint32_t)(gi * (a.gb / 2) + cc) * 16u;
             const uint32_t acc = fresh ? 0u : 1u;
+            if (a.diag != 101)
             asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(taddr),
                          "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
                          : "memory");
@@ -203,7 +225,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
         if (((k + 1) % kFlush) == 0 || k + 1 == my_tiles) umma_commit(tile_done);
       }
     }
-   } else if (warp == 18) {
+   } else if (warp == kCW + 2) {
     // ===================== scalar warp =====================
     double lossacc = 0.0, cntacc = 0.0;
     double ynext = 0.0;
@@ -224,7 +246,14 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
       named_sync(1 + bb, kConsumers + 32);                     // partial dots of tile k are in shared memory
       double mult = 0.0;
       if (lane < kKR) {
-        const double m = partial[(bb * kKR + lane) * 2] + partial[(bb * kKR + lane) * 2 + 1];
+        double m;
+        if (RPT) {
+          m = partial[(bb * kKR + lane) * 2] + partial[(bb * kKR + lane) * 2 + 1];
+        } else {  // one partial per consumer warp, fixed tree
+          const double *pp = partial + (bb * kKR + lane) * 16;
+          m = (((pp[0] + pp[1]) + (pp[2] + pp[3])) + ((pp[4] + pp[5]) + (pp[6] + pp[7]))) +
+              (((pp[8] + pp[9]) + (pp[10] + pp[11])) + ((pp[12] + pp[13]) + (pp[14] + pp[15])));
+        }
         double mu, loss;
         loss_eval(a.kind, m, ylab, mu, loss);
         if (lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + tile * kKR + lane)) {
@@ -255,10 +284,10 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
     }
     if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; }
    }
-  } else if (warp >= 20) {
+  } else if (warp >= kCW + 4) {
     // ===================== flush warpgroup: owns the fp64 gradient, drains TMEM every kFlush tiles ==========
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsFlush));
-    const int fw = warp - 20;       // TMEM lanes 32*fw .. 32*fw+31
+    if (kRepartition) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsFlush));
+    const int fw = warp - (kCW + 4);   // TMEM lanes 32*fw .. 32*fw+31 (kCW + 4 is a multiple of 4)
     double gacc[32];                // feature (c*128 + 32*fw + lane), c < d/128
 #pragma unroll
     for (int c = 0; c < 32; ++c) gacc[c] = 0.0;
@@ -290,8 +319,60 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
       if (c < nch) slab[c * 128 + fw * 32 + lane] = gacc[c];
   } else {
     // ===================== consumers: phase 1 in fp64, straight out of the swizzled tile =====================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
-    const int rq = tid >> 6;        // rows rq and rq + 8
+    if (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
+    if constexpr (RPT == 0) {
+      const int r = lane & 15, hsel = lane >> 4;
+      mbar_wait(wbar, 0);
+      int slot = -1;
+      uint32_t par = 1;
+      const int npairs = a.gb * 4;                       // pairs of adjacent 8-feature chunks per ring group
+      // this lane's chunk in task j: c = 2 * (warp + 16 j) + hsel; block c >> 3, 16-byte position (c & 7) ^ (row & 7)
+      uint32_t x_off[2];
+      int w_off[2];
+      bool act[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = 2 * (warp + 16 * j) + hsel;
+        act[j] = warp + 16 * j < npairs;
+        x_off[j] = (uint32_t)((c >> 3) * kBlockBytes + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+        w_off[j] = c * 8;
+      }
+      for (long long k = 0; k < my_tiles; ++k) {
+        const int bb = (int)(k & 1);
+        double pa[2] = {0.0, 0.0}, pb[2] = {0.0, 0.0};
+        const double *wp = w_s;
+        for (int gi = 0; gi < a.ngt; ++gi) {
+          if (++slot == RG) slot = 0;
+          if (slot == 0) par ^= 1u;
+          mbar_wait(bars + 8u * slot, par);
+          if (a.diag != 100) {
+            const unsigned char *gbase = smem + (uint32_t)slot * (uint32_t)group_bytes;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              if (act[j]) {
+                const uint4 xr = *reinterpret_cast<const uint4 *>(gbase + x_off[j]);
+                const double2 *wv = reinterpret_cast<const double2 *>(wp + w_off[j]);   // the same address on 16 lanes
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const double2 wq = wv[q];
+                  const uint32_t xw = q == 0 ? xr.x : q == 1 ? xr.y : q == 2 ? xr.z : xr.w;
+                  pa[j] = fma((double)__uint_as_float(xw << 16), wq.x, pa[j]);
+                  pb[j] = fma((double)__uint_as_float(xw & 0xffff0000u), wq.y, pb[j]);
+                }
+              }
+            }
+          }
+          wp += a.gb * 64;
+        }
+        double p = (pa[0] + pb[0]) + (pa[1] + pb[1]);
+        p += __shfl_xor_sync(0xffffffffu, p, 16);              // the two chunk columns of the warp
+        if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
+        if (lane < 16) partial[(bb * kKR + r) * 16 + warp] = p;
+        named_arrive(1 + bb, kConsumers + 32);
+      }
+    } else {
+    constexpr int kSlots = kKR / (RPT ? RPT : 1);   // thread (rq, vv) handles rows rq, rq + kSlots, ... of every tile
+    const int rq = tid >> 6;
     const int vv = tid & 63;        // 16-byte vector within the group row
     mbar_wait(wbar, 0);
     // one-time re-layout of w: within each 64-byte chunk c (8 features) swap the four 16-byte pairs j -> j ^ ((c>>1)&3)
@@ -310,40 +391,52 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a, const lon
     const int blk = vv >> 3, ch = vv & 7;
     const bool active = vv < a.gb * 8;
     const int sw = (lane >> 1) & 3;
-    const uint32_t x_off0 = (uint32_t)(blk * kBlockBytes + rq * 128 + ((ch ^ (rq & 7)) << 4));       // row rq
-    const uint32_t x_off1 = x_off0 + 8 * 128;                                                        // row rq + 8: same swizzle
+    uint32_t x_off[RPT];            // row rq + j * kSlots of a block: 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int row = rq + j * kSlots;
+      x_off[j] = (uint32_t)(blk * kBlockBytes + row * 128 + ((ch ^ (row & 7)) << 4));
+    }
     for (long long k = 0; k < my_tiles; ++k) {
       const int bb = (int)(k & 1);
-      double p0a = 0.0, p0b = 0.0, p1a = 0.0, p1b = 0.0;
+      double pa[RPT], pb[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) { pa[j] = 0.0; pb[j] = 0.0; }
       const double *wp = w_s + (blk * 64 + ch * 8);
       for (int gi = 0; gi < a.ngt; ++gi) {
         if (++slot == RG) slot = 0;
         if (slot == 0) par ^= 1u;
         mbar_wait(bars + 8u * slot, par);
-        if (active) {
+        if (active && a.diag != 100) {
           const unsigned char *gbase = smem + (uint32_t)slot * (uint32_t)group_bytes;
-          const uint4 r0 = *reinterpret_cast<const uint4 *>(gbase + x_off0);
-          const uint4 r1 = *reinterpret_cast<const uint4 *>(gbase + x_off1);
-          // w was re-laid out once per CTA (below): the 16-byte pair j of chunk c sits at position j ^ ((c >> 1) & 3), so
+          uint4 xr[RPT];
+#pragma unroll
+          for (int j = 0; j < RPT; ++j) xr[j] = *reinterpret_cast<const uint4 *>(gbase + x_off[j]);
+          // w was re-laid out once per CTA (above): the 16-byte pair j of chunk c sits at position j ^ ((c >> 1) & 3), so
           // the 8 lanes of a quarter-warp touch 8 different bank groups with no per-element shuffling of the x words
-          const uint32_t w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const double2 wq = *reinterpret_cast<const double2 *>(wp + 2 * (q ^ sw));  // features 2q, 2q+1 of this chunk
-            p0a = fma((double)__uint_as_float(w0[q] << 16), wq.x, p0a);
-            p0b = fma((double)__uint_as_float(w0[q] & 0xffff0000u), wq.y, p0b);
-            p1a = fma((double)__uint_as_float(w1[q] << 16), wq.x, p1a);
-            p1b = fma((double)__uint_as_float(w1[q] & 0xffff0000u), wq.y, p1b);
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+              const uint32_t xw = q == 0 ? xr[j].x : q == 1 ? xr[j].y : q == 2 ? xr[j].z : xr[j].w;
+              pa[j] = fma((double)__uint_as_float(xw << 16), wq.x, pa[j]);
+              pb[j] = fma((double)__uint_as_float(xw & 0xffff0000u), wq.y, pb[j]);
+            }
           }
         }
         wp += a.gb * 64;
       }
-      double p[2] = {p0a + p0b, p1a + p1b};
-      const double tot = warp_rows_reduce<2>(p, lane);        // lanes 0-15 hold row rq, lanes 16-31 row rq + 8
+      double p[RPT];
+#pragma unroll
+      for (int j = 0; j < RPT; ++j) p[j] = pa[j] + pb[j];
+      // afterwards the lanes of eighth/half-warp j hold the warp total of row rq + j * kSlots
+      const double tot = warp_rows_reduce<RPT>(p, lane);
       if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
-      if ((lane & 15) == 0) partial[(bb * kKR + rq + 8 * (lane >> 4)) * 2 + (warp & 1)] = tot;
+      if ((lane & (32 / RPT - 1)) == 0) partial[(bb * kKR + rq + kSlots * (lane / (32 / RPT))) * 2 + (warp & 1)] = tot;
       named_arrive(1 + bb, kConsumers + 32);
     }
+    }  // column-slice mapping
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;");
@@ -381,7 +474,21 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return cudaErrorInvalidValue;
+  CUtensorMap tmap3;
+  {
+    const cuuint64_t gdim3[3] = {64, (cuuint64_t)a.rows, (cuuint64_t)(a.d / 64)};
+    const cuuint64_t gstr3[2] = {(cuuint64_t)a.d * 2, 128};
+    const int nblk3 = a.d / 64;
+    const cuuint32_t box3[3] = {64, (cuuint32_t)kKR, (cuuint32_t)(nblk3 < 8 ? nblk3 : 8)};
+    const cuuint32_t estr3[3] = {1, 1, 1};
+    if (encode(&tmap3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(a.X), gdim3, gstr3, box3, estr3,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
   TcArgs t;
+  t.one_copy = a.tune_ctas == 2 ? 0 : 1;   // option ring_ctas=2: one 2-D copy per 64-feature block (slower: 8x the TMA operations)
+  t.diag = (a.kind == 100 || a.kind == 101) ? a.kind : 0;
   t.labels = a.labels; t.w = a.w; t.slabs = a.slabs; t.rows = a.rows; t.d = a.d; t.kind = a.kind;
   t.slab_stride = a.slab_stride;
   t.sample_seed = a.sample_seed; t.sample_thresh = a.sample_thresh; t.row_base = a.row_base;
@@ -398,13 +505,25 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
   while (cols < a.d / 8) cols <<= 1;
   t.tmem_cols = cols;
   const TcLayout L = tc_layout(ring, group_bytes, a.d);
-  cudaError_t e = cudaFuncSetAttribute(k1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total + 1024);
-  if (e != cudaSuccess) return e;
   const long long ntiles = (a.rows + kKR - 1) / kKR;
   long long grid = sm_count;
   if (grid > ntiles) grid = ntiles;
   *blocks_out = (int)grid;
-  k1_tc_kernel<<<(unsigned)grid, kThreads, L.total + 1024, st>>>(tmap, t, ntiles);
+  const int smem_bytes = (int)L.total + 1024;
+  cudaError_t e;
+  if (a.tune_rows == 1) {  // option ring_rows=1: row-per-lane consumers (broadcast w reads; measured slower)
+    e = cudaFuncSetAttribute(k1_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    k1_tc_kernel<0><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  } else if (a.tune_rows == 4) {  // option ring_rows=4: 256 consumers with four rows each (measured slower)
+    e = cudaFuncSetAttribute(k1_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    k1_tc_kernel<4><<<(unsigned)grid, 512, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  } else {  // default: 512 consumers, two rows per thread
+    e = cudaFuncSetAttribute(k1_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    k1_tc_kernel<2><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  }
   return cudaGetLastError();
 }
 

@@ -17,8 +17,13 @@ def t(label, grad, **opts):
     ms = st.k1_ms_total / st.k1_launches
     print(json.dumps(dict(label=label, rows=rows, d=d, **opts, k1_ms=round(ms, 3), gbs=round(bytes_pass / ms / 1e6, 1),
                           frac=round(bytes_pass / ms / 1e6 / 6566.1, 4), loss=h[-1])), flush=True)
-t("tc LS", S.LeastSquaresGradient(), k1_variant="tc")
+LS = S.LeastSquaresGradient()
+t("tc LS (default: 2 rows/thread, one 3-D copy per group)", LS, k1_variant="tc", ring_rows=0, ring_ctas=0, k1_diag=0)
 t("tc logistic", S.LogisticGradient())
-for st_ in (9, 10, 12):
-    t("tc LS", S.LeastSquaresGradient(), ring_stages=st_)
-t("ring LS", S.LeastSquaresGradient(), k1_variant="ring", ring_stages=0)
+t("tc LS, 4 rows/thread", LS, ring_rows=4)
+t("tc LS, row per lane", LS, ring_rows=1)
+t("tc LS, 2-D copies", LS, ring_rows=0, ring_ctas=2)
+t("diag: no consumer arithmetic", LS, ring_ctas=0, k1_diag=100)
+t("diag: no MMAs", LS, k1_diag=101)
+if len(sys.argv) > 3:
+    t("ring LS (CUDA cores)", LS, k1_variant="ring", k1_diag=0)
