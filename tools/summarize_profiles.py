@@ -40,15 +40,16 @@ def tobytes(s):
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
 
 summary = {}
-for tag, rep, rows, d, eb in [("k1_ring_logistic_10Mx1024_f32", "gpurun_out/k1_r1c_logistic_10M.ncu-rep", 10_000_000, 1024, 4),
-                              ("k1_tc_ls_3Mx4096_bf16", "gpurun_out/k1tc_r1b.ncu-rep", 3_000_000, 4096, 2)]:
+for tag, rep, rows, d, eb in [("k1_ring_logistic_10Mx1024_f32", "gpurun_out/k1_r1d_one.ncu-rep", 10_000_000, 1024, 4),
+                              ("k1_ring_two_point_logistic_10Mx1024_f32", "gpurun_out/k1_r1d_two.ncu-rep", 10_000_000, 1024, 4),
+                              ("k1_tc_ls_3Mx4096_bf16", "gpurun_out/k1tc_r1c.ncu-rep", 3_000_000, 4096, 2)]:
     if not os.path.exists(rep):
         continue
     m, name = raw(rep)
     summary[tag] = {"kernel": name, "rows": rows, "d": d, "metrics": m, "warp_stall_pct": stalls(rep),
                     "algorithmic_bytes": rows * (d * eb + 8)}
-    if tag.startswith("k1_ring"):
-        json.dump({"kernel": "k1_ring_kernel<float,256,256,1,8,2>", "rows": rows, "d": d,
+    if tag == "k1_ring_logistic_10Mx1024_f32":
+        json.dump({"kernel": "k1_ring_kernel<float,256,256,1,8,2,false>", "rows": rows, "d": d,
                    "dram_bytes_read": tobytes(m["dram__bytes_read.sum"]), "dram_bytes_write": tobytes(m["dram__bytes_write.sum"]),
                    "algorithmic_bytes": rows * (d * eb + 8), "gpu_time_ms_under_ncu": float(m["gpu__time_duration.sum"].split()[0]),
                    "source": "ncu --set full --clock-control none, tools/k1_prof.py logistic 10000000 (round 1)"},
