@@ -45,7 +45,7 @@ def parse():
                          "(--rows 100000000 --dim 1000000 --nnz 64)")
     ap.add_argument("--nnz", type=int, default=64, help="stored entries per row for hinge_csr")
     ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "p2p"],
-                    help="all-reduce of the d+2 doubles: NVLink peer-memory exchange (default when mappable) or NCCL")
+                    help="all-reduce of the d+4 doubles: NVLink peer-memory exchange (default when mappable) or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = auto)")

@@ -40,7 +40,7 @@ int k1_tc_supported(int32_t d, int elem_bytes);
 cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStream_t st);
 // ---------------------------------------------------------------- K2': one-shot all-reduce over NVLink peer memory
 // Every rank owns an exchange buffer xbuf[2][W][n] (+ flags[2][W]) that all peers can store into (P2P / CUDA IPC).
-// publish: rank r stores its n = d+2 partial sums into slot r of EVERY rank's buffer, fences, then raises the flag
+// publish: rank r stores its n = d+4 partial sums into slot r of EVERY rank's buffer, fences, then raises the flag
 // (epoch) -- fused into the tail of k1_reduce_kernel, or standalone for the CSR path.  gather: each rank waits for the
 // W flags of the epoch and adds the W slots in rank order, so every rank gets the same bits (replaces combOp +
 // treeAggregate + broadcast, AGD.scala:193-204, without a library call in the loop).  Buffers alternate by epoch parity.
