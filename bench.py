@@ -5,9 +5,10 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K --warmup W
 
-A "step" is one outer AGD iteration (AGD.scala:237-332) = 3 + 2b applySmooth passes over the shard
-with the reference's exact pass structure (flags = 0).  `value` = examples/sec = total rows x passes
-executed / time, shards resident in HBM when the timed region starts.  `e2e` is the same metric through
+A "step" is one outer AGD iteration (AGD.scala:237-332) = the reference's 3 + 2b applySmooth evaluations
+(flags = 0: every evaluation is executed; the history evaluation of :304 shares one sweep over X with the next
+iteration's applySmooth(y), see `fused_passes` / `sweeps` / `unfused` in the output).  `value` = examples/sec =
+total rows x evaluations executed / time, shards resident in HBM when the timed region starts.  `e2e` is the same metric through
 the public call with HOST buffers: the shard upload from pinned host memory (what `.cache()` pays),
 the run, and the results coming back are all inside its timed region.
 """
