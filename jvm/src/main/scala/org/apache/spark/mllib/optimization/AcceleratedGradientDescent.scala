@@ -33,6 +33,11 @@ class AcceleratedGradientDescent(private var gradient: Gradient, private var upd
 
 @DeveloperApi
 object AcceleratedGradientDescent {
+  /** agd_params.flags (include/agd_b200.h): 0 = every applySmooth evaluation of the reference is executed, the history
+    * evaluation sharing one sweep over the shards with the next iteration's first one (bit-identical results);
+    * -Dagd.flags=1 (AGD_FLAG_MEMOIZE_FX) / 2 (AGD_FLAG_NO_FUSE) select the other pass structures. */
+  private def flags: Int = sys.props.get("agd.flags").map(_.trim.toInt).getOrElse(0)
+
   /** GPUs of this box; override with -Dagd.devices=0,1,... */
   private def devices: Array[Int] =
     sys.props.get("agd.devices").map(_.split(',').map(_.trim.toInt)).getOrElse(Array(0))
@@ -64,7 +69,7 @@ object AcceleratedGradientDescent {
       }
       val w = initialWeights.toArray.clone()
       val history = NativeAGD.run(handle, g, u, convergenceTol, numIterations, regParam, w, L0, Lexact, beta, alpha,
-        mayRestart, 0)
+        mayRestart, flags)
       (Vectors.dense(w), history)
     } finally NativeAGD.destroy(handle)
   }
