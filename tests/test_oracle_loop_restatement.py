@@ -169,3 +169,37 @@ def test_c_oracle_equals_python_restatement_bit_for_bit(oracle, grad, upd, reg, 
     assert (st["passes"], st["backtracks"], st["restarts"]) == (ref.passes, ref.backtracks, ref.restarts)
     assert np.array_equal(np.array(hist), ref.loss_history)
     assert np.array_equal(np.array(w), ref.weights)
+
+
+def py_gd_run(X, y, grad, upd, w0, step_size, iters, reg, parts=2):
+    """GradientDescent.runMiniBatchSGD [mllib-1.3.0] with miniBatchFraction = 1.0 (the comparator of Suite.scala:78,118,225)."""
+    n, d = len(X), len(w0)
+    w = list(w0)
+    _, reg_val = updater_compute(upd, w, [0.0] * d, 0.0, reg)
+    hist = []
+    for i in range(1, iters + 1):
+        partials = []
+        for p in range(parts):
+            lo, hi = (p * n) // parts, ((p + 1) * n) // parts
+            loss, g, cnt = 0.0, [0.0] * d, 0
+            for r in range(lo, hi):
+                loss = loss + gradient_compute(grad, X[r], y[r], w, g)
+                cnt += 1
+            partials.append((loss, g, cnt))
+        loss, g, cnt = partials[0]
+        for l2, g2, c2 in partials[1:]:
+            loss, g, cnt = loss + l2, [g[j] + g2[j] for j in range(d)], cnt + c2
+        hist.append(loss / cnt + reg_val)
+        w, reg_val = updater_compute(upd, w, [v / float(cnt) for v in g], step_size / math.sqrt(i), reg)
+    return w, hist
+
+
+@pytest.mark.parametrize("grad,upd,reg", [("logistic", "simple", 0.0), ("logistic", "squared_l2", 0.2), ("least_squares", "l1", 0.05),
+                                          ("hinge", "squared_l2", 0.1)])
+def test_c_oracle_gd_equals_python_restatement_bit_for_bit(oracle, grad, upd, reg):
+    rng = np.random.default_rng(len(grad) + 7 * len(upd))
+    X, y = make(rng, 90, 4, grad)
+    w, hist = py_gd_run(X.tolist(), y.tolist(), grad, upd, [0.1, -0.2, 0.0, 0.3], 0.5, 30, reg)
+    rw, rhist = oracle.gd_run(oracle.Data(y, X=X), grad, upd, np.array([0.1, -0.2, 0.0, 0.3]), step_size=0.5, num_iterations=30,
+                              reg_param=reg, partitions=2)
+    assert np.array_equal(np.array(hist), rhist) and np.array_equal(np.array(w), rw)
