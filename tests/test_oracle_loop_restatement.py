@@ -203,3 +203,23 @@ def test_c_oracle_gd_equals_python_restatement_bit_for_bit(oracle, grad, upd, re
     rw, rhist = oracle.gd_run(oracle.Data(y, X=X), grad, upd, np.array([0.1, -0.2, 0.0, 0.3]), step_size=0.5, num_iterations=30,
                               reg_param=reg, partitions=2)
     assert np.array_equal(np.array(hist), rhist) and np.array_equal(np.array(w), rw)
+
+
+def test_c_oracle_sparse_rows_equal_python_on_the_densified_matrix(oracle):
+    """SparseVector rows take the sparse branches of BLAS.dot / BLAS.axpy [mllib-1.3.0] (stored entries only, index order).
+    Skipped zeros contribute exact zeros, so the CSR oracle must match the dense Python restatement bit for bit."""
+    rng = np.random.default_rng(99)
+    n, d, k = 80, 12, 4
+    idx = np.sort(np.stack([rng.choice(d, k, replace=False) for _ in range(n)]), axis=1).astype(np.int32)
+    val = rng.standard_normal((n, k))
+    rowptr = np.arange(n + 1, dtype=np.int64) * k
+    Xd = np.zeros((n, d))
+    for i in range(n):
+        Xd[i, idx[i]] = val[i]
+    y = (Xd @ rng.standard_normal(d) > 0).astype(float)
+    for grad, upd, reg in (("hinge", "squared_l2", 0.1), ("logistic", "l1", 0.01)):
+        w, hist, st = py_agd_run(Xd.tolist(), y.tolist(), grad, upd, [0.0] * d, 0.0, 20, reg)
+        ref = oracle.agd_run(oracle.Data(y, csr=(rowptr, idx.ravel(), val.ravel()), d=d), grad, upd, np.zeros(d),
+                             convergence_tol=0.0, num_iterations=20, reg_param=reg, partitions=2)
+        assert (st["passes"], st["backtracks"], st["restarts"]) == (ref.passes, ref.backtracks, ref.restarts)
+        assert np.array_equal(np.array(hist), ref.loss_history) and np.array_equal(np.array(w), ref.weights)
