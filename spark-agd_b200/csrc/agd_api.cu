@@ -470,7 +470,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
       a.rowptr = s.rowptr; a.idx = s.idx; a.val = s.val; a.labels = s.labels; a.w = w_of(D);
       a.w2 = w2_of ? w2_of(D) : nullptr;
       a.gacc = D.acc; a.rows = s.rows; a.d = d; a.kind = kind;
-      a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base;
+      a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune = h->tune_rows;
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
       CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));

@@ -79,6 +79,7 @@ struct K1CsrArgs {
   int32_t kind;
   unsigned long long sample_seed, sample_thresh;
   long long row_base;
+  int32_t tune;           // option ring_rows: 1 = the simple (unpipelined) loop
 };
 cudaError_t k1_csr_launch(const K1CsrArgs &a, int elem_bytes, int sm_count, cudaStream_t st);
 

@@ -278,6 +278,7 @@ def test_csr_smooth_matches_oracle(agd, ctx, oracle, grad, store):
     n, d = 3000, 5000
     nnz_row = rng.integers(0, 40, size=n)
     nnz_row[5] = 0
+    nnz_row[7], nnz_row[8], nnz_row[9], nnz_row[n - 1] = 64, 65, 200, 33      # around the two-entries-per-lane fast path
     rowptr = np.concatenate([[0], np.cumsum(nnz_row)]).astype(np.int64)
     idx = np.concatenate([np.sort(rng.choice(d, size=k, replace=False)) for k in nnz_row]).astype(np.int32)
     val = rng.standard_normal(rowptr[-1]).astype(np.float32 if store == "f32" else np.float64)
@@ -289,6 +290,10 @@ def test_csr_smooth_matches_oracle(agd, ctx, oracle, grad, store):
     assert cnt == n
     np.testing.assert_allclose(loss, ref_loss, rtol=1e-12)
     assert rel_err(g, ref_g) < 1e-12
+    ds.set_option("ring_rows", 1)                     # the simple (unpipelined) row loop
+    loss1, g1, _ = ds.smooth(G(agd, grad), w)
+    np.testing.assert_allclose(loss1, loss, rtol=1e-14)   # same per-row arithmetic; only the order of the atomic sums differs
+    assert rel_err(g1, g) < 1e-14
     ds.close()
 
 

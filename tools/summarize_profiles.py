@@ -9,7 +9,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum"]
+        "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "lts__t_sectors.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 def raw(rep):
     out = subprocess.run(f"ncu -i {rep} --page raw --csv", shell=True, capture_output=True, text=True).stdout
@@ -42,12 +45,14 @@ def tobytes(s):
 summary = {}
 for tag, rep, rows, d, eb in [("k1_ring_logistic_10Mx1024_f32", "gpurun_out/k1_r1d_one.ncu-rep", 10_000_000, 1024, 4),
                               ("k1_ring_two_point_logistic_10Mx1024_f32", "gpurun_out/k1_r1d_two.ncu-rep", 10_000_000, 1024, 4),
-                              ("k1_tc_ls_3Mx4096_bf16", "gpurun_out/k1tc_r1c.ncu-rep", 3_000_000, 4096, 2)]:
+                              ("k1_tc_ls_3Mx4096_bf16", "gpurun_out/k1tc_r1c.ncu-rep", 3_000_000, 4096, 2),
+                              ("k1_csr_hinge_4Mx1M_64nnz_f32", "gpurun_out/k1csr_r1.ncu-rep", 4_000_000, 1_000_000, 4)]:
     if not os.path.exists(rep):
         continue
     m, name = raw(rep)
+    csr = tag.startswith("k1_csr")
     summary[tag] = {"kernel": name, "rows": rows, "d": d, "metrics": m, "warp_stall_pct": stalls(rep),
-                    "algorithmic_bytes": rows * (d * eb + 8)}
+                    "algorithmic_bytes": rows * (64 * (4 + eb) + 16) if csr else rows * (d * eb + 8)}
     if tag == "k1_ring_logistic_10Mx1024_f32":
         json.dump({"kernel": "k1_ring_kernel<float,256,256,1,8,2,false>", "rows": rows, "d": d,
                    "dram_bytes_read": tobytes(m["dram__bytes_read.sum"]), "dram_bytes_write": tobytes(m["dram__bytes_write.sum"]),
