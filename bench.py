@@ -49,7 +49,13 @@ def parse():
                     help="all-reduce of the d+4 doubles: NVLink peer-memory exchange (default when mappable) or NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = 4M, the same at every N)")
+    ap.add_argument("--store", default="f32", choices=["f32", "bf16"],
+                    help="HBM storage of the logistic_f32 workload; bf16 is the stated substitute that lets the 100M x 512 "
+                         "shape of configs[4] fit ONE GPU (204.8 GB as fp32)")
+    ap.add_argument("--parity-iters", type=int, default=10,
+                    help="iterations of the full-size oracle comparison reported as `parity` (0 = off; on by default for "
+                         "fp32 logistic workloads whose host copy is <= 64 GB)")
     return ap.parse_args()
 
 
@@ -111,40 +117,49 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ reference arm
-def cpu_reference(rows: int, d: int, steps: int, warmup: int, X=None, y=None):
-    """Times the reference's CPU path (the oracle port: treeAggregate-shaped fp64 fold, one partition
-    per host thread) on a bounded sample of the same workload."""
+CPU_SAMPLE_ROWS = 4_000_000     # the bounded sample is the same at every N (the arm must be reproducible)
+
+
+def cpu_sample_rows(args) -> int:
+    return max(1000, min(args.cpu_rows or CPU_SAMPLE_ROWS, args.rows))
+
+
+def cpu_reference(rows: int, d: int, steps: int, warmup: int, repeats: int = 3):
+    """Times the reference's CPU path (the oracle port: treeAggregate-shaped fp64 fold, one partition per host thread)
+    on a bounded sample of the same workload.  Reproducibility: thread count from the affinity mask (torchrun exports
+    OMP_NUM_THREADS=1), every OpenMP thread pinned to one CPU, the sample generated by the thread that folds it (first
+    touch => NUMA-local), and the median of `repeats` timed runs."""
     from oracle import oracle as O
-    cores = O.max_threads()
-    if X is None:
-        X = O.synth_dense_f32(SEED, 0, rows, d)
+    cores = O.host_threads()
+    O.bind_threads(cores)
+    try:
+        X = O.synth_dense_f32_placed(SEED, 0, rows, d, cores, cores)     # first `rows` rows of the workload
         y = O.synth_labels(SEED, "logistic", 0, X, O.synth_wtrue(SEED, d))
-    D = O.Data(y, X=X)
-    w0 = np.zeros(d)
-    if warmup > 0:
-        O.agd_run(D, "logistic", "simple", w0, convergence_tol=0.0, num_iterations=warmup, partitions=cores, threads=cores)
-    t0 = time.perf_counter()
-    r = O.agd_run(D, "logistic", "simple", w0, convergence_tol=0.0, num_iterations=steps, partitions=cores, threads=cores)
-    dt = time.perf_counter() - t0
+        D = O.Data(y, X=X)
+        w0 = np.zeros(d)
+        kw = dict(convergence_tol=0.0, partitions=cores, threads=cores)
+        if warmup > 0:
+            O.agd_run(D, "logistic", "simple", w0, num_iterations=warmup, **kw)
+        runs = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            r = O.agd_run(D, "logistic", "simple", w0, num_iterations=steps, **kw)
+            runs.append(time.perf_counter() - t0)
+    finally:
+        O.unbind_threads()
+    dt = sorted(runs)[len(runs) // 2]
     return {"value": rows * r.passes / dt, "unit": "examples/s", "cores": cores, "kind": "port",
-            "sample": f"first {rows} rows of the workload x {steps} AGD iterations ({r.passes} passes), "
-                      f"{cores} partitions on {cores} threads, fp32 rows upcast to fp64",
-            "seconds": dt, "iters_per_sec": r.iterations / dt, "passes": r.passes, "rows": rows}
-
-
-def auto_cpu_rows(cores: int, d: int, rows_total: int) -> int:
-    # ~7 us per row-pass per thread at d = 1024 (sequential fp64 dot + axpy); aim at ~1 s per pass
-    est = int(1.4e5 * cores * 1024 / d)
-    return max(1000, min(rows_total, est, 4_000_000))
+            "sample": f"first {rows} rows of the workload x {steps} AGD iterations ({r.passes} passes), median of "
+                      f"{repeats} timed runs, {cores} partitions on {cores} pinned threads, first-touch placement, "
+                      f"fp32 rows upcast to fp64",
+            "seconds": dt, "runs_seconds": runs, "iters_per_sec": r.iterations / dt, "passes": r.passes, "rows": rows}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    cores = O.max_threads()
-    rows = args.cpu_rows or auto_cpu_rows(cores, args.dim, args.rows)
+    rows = cpu_sample_rows(args)
     steps = max(1, min(args.steps, 4))        # each step is a bounded sample; keep the arm within minutes
     warm = 1 if args.warmup > 0 else 0
     res = cpu_reference(rows, args.dim, steps, warm)
@@ -156,7 +171,7 @@ def run_reference(args):
                    "sample_rows": rows, "note": "staple/spark-agd needs a JVM + Spark 1.3.0 (absent): this arm times the "
                    "repo's C restatement of its treeAggregate path (oracle/), an optimistic stand-in"},
         "iters_per_sec": res["iters_per_sec"],
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "runs_seconds")},
         "e2e": {"value": res["value"], "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -199,7 +214,8 @@ def run_b200(args):
     wl = args.workload
     reg = 0.0
     if wl == "logistic_f32":
-        grad, upd, store, eb = S.LogisticGradient(), S.SimpleUpdater(), "f32", 4
+        store = args.store
+        grad, upd, eb = S.LogisticGradient(), S.SimpleUpdater(), (4 if store == "f32" else 2)
         data = ctx.synthetic(total_rows, d, grad, seed=SEED, store=store)     # K0: never timed
     elif wl == "ls_bf16":
         grad, upd, store, eb = S.LeastSquaresGradient(), S.SimpleUpdater(), "bf16", 2
@@ -211,9 +227,11 @@ def run_b200(args):
     w0 = np.zeros(d)
     if args.collective != "auto":
         data.set_option("collective", args.collective)
-    if wl != "logistic_f32":
+    headline = wl == "logistic_f32" and store == "f32"
+    if not headline:
         args.no_e2e = True
         args.no_cpu_baseline = True
+    parity_iters = args.parity_iters if (headline and total_rows * d * 4 <= (64 << 30)) else 0
 
     def run(ds, iters, memoize=False, fuse=True):
         return S.run_with_stats(ds, grad, upd, 0.0, iters, reg, w0, memoize=memoize, fuse=fuse)
@@ -252,43 +270,44 @@ def run_b200(args):
     else:
         alg_bytes = rows_local * (d * eb + 8)     # stored row + fp64 label, per launch
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
-    kname = {"logistic_f32": "k1_ring_kernel<float,...>", "ls_bf16": "k1_ring_kernel<__nv_bfloat16,...>",
-             "hinge_csr": "k1_csr_kernel<float>"}[wl]
+    kname = data.kernel_name()                      # the K1 kernel this shard actually dispatches to
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows_local, d) if wl == "logistic_f32" else None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(rows_local, d) if headline else None,
                 "peak_source": peak_src, "bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
                 "launches": int(st.k1_launches), "two_point_launches": int(n_two),
                 "ms_per_launch_one_point": k1_ms_single, "ms_per_launch_two_point": k1_ms_two,
                 "frac_one_point": alg_bytes / (k1_ms_single * 1e-3) / 1e9 / peak,
                 "k1_share_of_step": st.k1_ms_total / st.device_ms_total}
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N = 1 only
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        cores = O.max_threads()
-        n_s = min(args.cpu_rows or auto_cpu_rows(cores, d, total_rows), rows_local)
-        Xs, ys = data.get_rows(0, 0, n_s)           # the very rows the GPU holds
-        res = cpu_reference(n_s, d, 2, 0, Xs, ys)
-        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-
     # ---- e2e: public call with HOST buffers; shard upload + run + results inside the timed region
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(S, ctx, data, rows_local, total_rows, d, args, run, barrier, max_over_ranks, world)
 
+    # ---- parity on the FULL workload (every N): the same loop on the GPU path and on the oracle, same rows
+    parity = None
+    if parity_iters > 0:
+        parity = measure_parity(S, data, run, parity_iters, total_rows, rows_local, d, rank, world, barrier)
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N = 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_reference(cpu_sample_rows(args), d, 2, 1)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "runs_seconds")}
+
     if rank == 0:
+        wl_text = {"logistic_f32": f"logistic-loss AGD, {total_rows} x {d} dense {'fp32' if store == 'f32' else 'bf16 storage'} "
+                                   f"({'BASELINE configs[1]' if (total_rows, d) == (10_000_000, 1024) else 'BASELINE configs[4] shape'}), "
+                                   f"SimpleUpdater, w0 = 0, convergenceTol 0, defaults L0=1 beta=.5 alpha=.9 restart",
+                   "ls_bf16": f"least-squares AGD, {total_rows} x {d} dense bf16 storage (BASELINE configs[3] shape), kernel {kname}",
+                   "hinge_csr": f"hinge-loss + L2 (reg 0.1) AGD, {total_rows} x {d} CSR, {args.nnz} stored entries per "
+                                f"row (BASELINE configs[2] shape)"}[wl]
         line = {
-            "metric": METRIC if (wl == "logistic_f32" and total_rows == 10_000_000 and d == 1024) else
-            f"AGD examples/sec (rows x applySmooth passes / s), {wl} {total_rows} x {d}", "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if (headline and total_rows == 10_000_000 and d == 1024) else
+            f"AGD examples/sec (rows x applySmooth passes / s), {wl} {total_rows} x {d} store {store}", "value": value, "unit": "examples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": {"logistic_f32": f"logistic-loss AGD, {total_rows} x {d} dense fp32 (BASELINE configs[1]), "
-                                                    f"SimpleUpdater, w0 = 0, convergenceTol 0, defaults L0=1 beta=.5 alpha=.9 restart",
-                                    "ls_bf16": f"least-squares AGD, {total_rows} x {d} dense bf16 storage (BASELINE configs[3] shape), "
-                                               f"CUDA-core fp64 path",
-                                    "hinge_csr": f"hinge-loss + L2 (reg 0.1) AGD, {total_rows} x {d} CSR, {args.nnz} stored entries per "
-                                                 f"row (BASELINE configs[2] shape)"}[wl],
+            "config": {"workload": wl_text,
                        "rows": total_rows, "d": d, "store": store, "rows_per_gpu": rows_local,
                        "parallelism": f"row shards x{world}, one all-reduce of d+4 fp64 per sweep",
                        "accounting": "value = rows x applySmooth evaluations / s (the reference's unit of work, 3 + 2b per "
@@ -305,10 +324,10 @@ def run_b200(args):
                         "sweeps": int(st_u.k1_launches), "loss_history_bit_identical_to_fused": same_bits,
                         "note": "AGD_FLAG_NO_FUSE: same weights and history bit for bit, 3 + 2b reads of X per iteration"},
             "memoized": {"iters_per_sec": st_m.iterations / dev_s_m, "passes_per_iter": st_m.passes / st_m.iterations,
-                         "examples_per_sec": total_rows * st_m.passes / dev_s_m,
+                         "examples_per_sec": total_rows * st_m.passes / dev_s_m, "sweeps": int(st_m.k1_launches),
                          "note": "AGD_FLAG_MEMOIZE_FX: same weights and history bit for bit, fewer passes"},
             "allreduce_ms_per_pass": st.allreduce_ms_total / max(st.collective_calls, 1),
-            "host_wall_s": st.seconds_total, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "host_wall_s": st.seconds_total, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,
             "gpu_launches": int(st.gpu_launches), "collective_calls": int(st.collective_calls),
             "collective": ("none" if world == 1 else ("nvlink peer-memory exchange" if st.collective_kind == 1 else "nccl all-reduce")),
             "clocks": clocks,
@@ -317,6 +336,76 @@ def run_b200(args):
     data.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_parity(S, data, run, iters, total_rows, rows_local, d, rank, world, barrier):
+    """north_star's acceptance line on the metric's own configuration: `iters` iterations of the same loop on the GPU
+    path (all ranks, the shards already resident) and on the oracle (rank 0, all host threads) over the SAME total_rows
+    rows; weights (AGD.scala:337) and the whole loss history (:304-306) compared.  The oracle's rows come from the CPU
+    twin of the on-device generator (bit-identical by construction, tests/test_synth_spec.py); every rank re-checks
+    that claim on the head and the tail of its own shard as downloaded from HBM, and the labels are the ones the GPUs
+    hold.  Partition order: the oracle folds `cores` contiguous partitions in order, the GPUs fold CTA slabs and then
+    ranks in order -- both are AGD.scala:201-204 combOp orders, different roundings of the same sums."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    barrier()
+    w_g, hist_g, st_g = run(data, iters)
+    # every rank: (a) its shard's head / tail rows against the twin at the shard's global offset, (b) its labels
+    row_lo = (rank * total_rows) // world
+    chk = min(1024, rows_local)
+    ok = 1
+    if chk > 0:
+        for r0 in (0, rows_local - chk):
+            xs, _ = data.get_rows(0, r0, chk)
+            ok &= int(np.array_equal(xs, O.synth_dense_f32(SEED, row_lo + r0, chk, d)))
+    y_loc = data.get_labels(0, 0, rows_local)
+    if world > 1:
+        t_ok = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        ok = int(t_ok.item())
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([rows_local], dtype=torch.int64, device="cuda"))
+        sizes = [int(t.item()) for t in sizes]
+        pad = torch.zeros(max(sizes), dtype=torch.float64, device="cuda")
+        pad[:rows_local] = torch.from_numpy(y_loc).cuda()
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        y = np.concatenate([p[:n].cpu().numpy() for p, n in zip(parts, sizes)]) if rank == 0 else None
+    else:
+        y = y_loc
+    out = None
+    if rank == 0:
+        cores = O.host_threads()
+        O.bind_threads(cores)
+        try:
+            t0 = time.perf_counter()
+            X = O.synth_dense_f32_placed(SEED, 0, total_rows, d, cores, cores)
+            t_gen = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            ref = O.agd_run(O.Data(y, X=X), "logistic", "simple", np.zeros(d), convergence_tol=0.0, num_iterations=iters,
+                            partitions=cores, threads=cores)
+            t_ref = time.perf_counter() - t0
+        finally:
+            O.unbind_threads()
+        del X
+        n = min(len(hist_g), len(ref.loss_history))
+        loss_err = float(np.max(np.abs(hist_g[:n] - ref.loss_history[:n]) / np.abs(ref.loss_history[:n]))) if n else None
+        out = {"rows": int(total_rows), "d": int(d), "iters": int(iters), "n_gpus": int(world),
+               "w_rel_err": float(np.linalg.norm(w_g - ref.weights) / np.linalg.norm(ref.weights)),
+               "w_max_abs_err": float(np.max(np.abs(w_g - ref.weights))),
+               "max_loss_rel_err": loss_err, "history_len_equal": bool(len(hist_g) == len(ref.loss_history)),
+               "passes_equal": bool(st_g.passes == ref.passes), "backtracks_equal": bool(st_g.backtracks == ref.backtracks),
+               "restarts_equal": bool(st_g.restarts == ref.restarts), "passes": int(st_g.passes),
+               "final_loss_gpu": float(hist_g[-1]), "final_loss_oracle": float(ref.loss_history[-1]),
+               "shards_equal_cpu_twin": bool(ok), "tolerance": "north_star: weights within 1e-5 relative after equal iterations",
+               "pass": bool(ok and len(hist_g) == len(ref.loss_history) and
+                            np.linalg.norm(w_g - ref.weights) / np.linalg.norm(ref.weights) <= 1e-5 and (loss_err or 0) <= 1e-9),
+               "oracle": {"cores": cores, "partitions": cores, "seconds": t_ref, "generate_seconds": t_gen,
+                          "examples_per_sec": total_rows * ref.passes / t_ref,
+                          "note": "the FULL workload on the host: every row, all threads (not the bounded sample of cpu_baseline)"}}
+    barrier()
+    return out
 
 
 def measure_e2e(S, ctx, data, rows_local, total_rows, d, args, run, barrier, max_over_ranks, world):

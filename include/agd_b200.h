@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AGD_B200_ABI_VERSION 1
+#define AGD_B200_ABI_VERSION 2
 
 typedef struct agd_handle agd_handle;
 
@@ -99,13 +99,29 @@ int agd_destroy(agd_handle *h);
 const char *agd_last_error(const agd_handle *h);
 
 /* ---- the collective (replaces treeAggregate + broadcast, AGD.scala:193,196-204) ----
- * One rank per GPU.  With a single process owning all GPUs nothing needs to be called (agd_create
- * builds the communicator).  With one process per GPU (torchrun / one executor per GPU): rank 0
+ * One rank per GPU.  With a single process owning all GPUs nothing needs to be called (the local GPUs
+ * are a complete world: direct peer pointers, NCCL only as a fallback); calling agd_comm_init on such a
+ * handle replaces that default, e.g. two processes with two GPUs each = world 4.  With one process per GPU (torchrun / one executor per GPU): rank 0
  * calls agd_comm_unique_id, ships the 128 bytes to every process, and every process calls
  * agd_comm_init(h, id, world_ranks, first_rank) where its local GPUs take ranks
  * first_rank .. first_rank + n_dev - 1. */
 int agd_comm_unique_id(void *out128);
 int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t first_rank);
+/* The same world WITHOUT NCCL.  The per-pass exchange never uses a library (P2P stores + epoch flags into peer HBM,
+ * csrc/xchg.cu); only its setup needs every rank to learn every other rank's CUDA IPC handles, and the host language can
+ * ship those itself (a Spark driver collecting one small blob per executor; torch.distributed / gloo in the tests):
+ *   1. every process:          agd_comm_init_ipc(h, world_ranks, first_rank)
+ *   2. after loading its shards (the feature dimension sizes the buffers):
+ *                              agd_xchg_export(h, blob, capacity, &n)   -> n = local GPUs * AGD_XCHG_HANDLE_BYTES
+ *   3. host: concatenate every process's blob in rank order, hand the whole to every process:
+ *                              agd_xchg_import(h, all, world_ranks * AGD_XCHG_HANDLE_BYTES)
+ * Works between processes on different GPUs (NVLink / PCIe P2P) and between processes sharing ONE GPU (CUDA IPC on the
+ * same device), which is how the 1-GPU test box exercises this path.  There is no fallback in such a world: if a pair
+ * of ranks cannot map each other, agd_xchg_import fails.  Steps 2-3 are repeated after agd_clear + a load with another d. */
+#define AGD_XCHG_HANDLE_BYTES 192
+int agd_comm_init_ipc(agd_handle *h, int32_t world_ranks, int32_t first_rank);
+int agd_xchg_export(agd_handle *h, void *out, int64_t capacity_bytes, int64_t *bytes_written);
+int agd_xchg_import(agd_handle *h, const void *all_ranks, int64_t bytes);
 
 /* ---- shard loading (replaces RDD[(Double, Vector)] partitions cached on executors, AGD.scala:178) ----
  * agd_reserve fixes the shard geometry of local device `dev` and allocates HBM for `rows_capacity`
@@ -188,6 +204,9 @@ int agd_gd_run(agd_handle *h, int32_t gradient, int32_t updater, double step_siz
 int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, double step_size, int32_t num_iterations,
                          double reg_param, double mini_batch_fraction, const double *w0, double *w_out,
                          double *loss_hist, int32_t *n_hist, agd_stats *stats);
+
+/* Name of the gradient kernel the shard on local device `dev` dispatches to (for reports), "" when empty. */
+const char *agd_kernel_name(const agd_handle *h, int32_t dev);
 
 /* Options: "k1_variant" = auto|ring|generic|ws|tc, "collective" = auto|nccl|p2p, ring tuning knobs. */
 int agd_set_option(agd_handle *h, const char *key, const char *value);

@@ -40,6 +40,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#ifdef __linux__
+#include <sched.h> /* sched_setaffinity: the Makefile passes -D_GNU_SOURCE */
+#endif
 
 #include "agd_oracle.h"
 
@@ -140,9 +143,10 @@ int oracle_smooth(const oracle_data *D, int grad_kind, const double *w, int part
   if (!pg || !pl || !pc) { free(pg); free(pl); free(pc); return -1; }
   (void)threads;
   /* per-partition sequential fold (seqOp AGD.scala:197-200); partition p owns the
-     ParallelCollectionRDD slice [p*n/P, (p+1)*n/P). */
+     ParallelCollectionRDD slice [p*n/P, (p+1)*n/P).  Partition p always runs on thread p % threads (the result does
+     not depend on the mapping -- the combine below is ordered -- but the CPU timing on a NUMA host does). */
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
+#pragma omp parallel for schedule(static, 1) num_threads(threads > 0 ? threads : 1)
 #endif
   for (int p = 0; p < P; ++p) {
     int64_t lo = (int64_t)(((__int128)p * D->n) / P), hi = (int64_t)(((__int128)(p + 1) * D->n) / P);
@@ -482,6 +486,61 @@ void oracle_generate_gd_input(double offset, double scale, int32_t n_points, int
     double y_val = offset + scale * x1[i] + r_logis;
     y[i] = (y_val > 0) ? 1.0 : 0.0;
   }
+}
+
+/* ---------- CPU-timing hygiene (bench.py's reference arm): thread pinning and first-touch placement ---------- */
+/* Pins OpenMP thread t of a `threads`-wide team to the t-th CPU of the process's affinity mask (the master too, until
+ * oracle_unbind_threads).  libgomp keeps its pool between regions of the same width, so the folds that follow run on
+ * the same cores that first-touched their partitions.  Returns the number of CPUs in the mask. */
+#ifdef __linux__
+static cpu_set_t g_saved_mask;
+static int g_have_saved_mask = 0;
+#endif
+int oracle_bind_threads(int threads) {
+#if defined(__linux__) && defined(_OPENMP)
+  cpu_set_t mask;
+  if (sched_getaffinity(0, sizeof mask, &mask) != 0) return -1;
+  if (!g_have_saved_mask) { g_saved_mask = mask; g_have_saved_mask = 1; }
+  else mask = g_saved_mask;
+  int cpus[CPU_SETSIZE], nc = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c)
+    if (CPU_ISSET(c, &mask)) cpus[nc++] = c;
+  if (nc == 0) return -1;
+#pragma omp parallel num_threads(threads > 0 ? threads : 1)
+  {
+    cpu_set_t one;
+    CPU_ZERO(&one);
+    CPU_SET(cpus[omp_get_thread_num() % nc], &one);
+    sched_setaffinity(0, sizeof one, &one);
+  }
+  return nc;
+#else
+  (void)threads;
+  return 0;
+#endif
+}
+void oracle_unbind_threads(void) { /* gives the calling (master) thread its original mask back */
+#if defined(__linux__) && defined(_OPENMP)
+  if (g_have_saved_mask) sched_setaffinity(0, sizeof g_saved_mask, &g_saved_mask);
+#endif
+}
+/* Zero-fills rows*row_bytes at `base` partition by partition in oracle_smooth's thread mapping (first touch). */
+void oracle_first_touch(void *base, int64_t rows, int64_t row_bytes, int partitions, int threads) {
+  const int P = partitions < 1 ? 1 : partitions;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(threads > 0 ? threads : 1)
+#endif
+  for (int p = 0; p < P; ++p) {
+    const int64_t lo = (int64_t)(((__int128)p * rows) / P), hi = (int64_t)(((__int128)(p + 1) * rows) / P);
+    memset((char *)base + lo * row_bytes, 0, (size_t)((hi - lo) * row_bytes));
+  }
+}
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 int oracle_max_threads(void) {

@@ -76,9 +76,16 @@ void oracle_jrandom_fill_double(int64_t seed, int64_t n, double *out);
 int oracle_jrandom_continue_fill_double(oracle_jrandom *r, int64_t n, double *out);
 void oracle_generate_gd_input(double offset, double scale, int32_t n_points, int32_t seed, double *x1, double *y);
 int oracle_max_threads(void);
+/* CPU-timing hygiene for bench.py's reference arm (thread pinning, first-touch placement) */
+int oracle_bind_threads(int threads);
+void oracle_unbind_threads(void);
+void oracle_first_touch(void *base, int64_t rows, int64_t row_bytes, int partitions, int threads);
+void oracle_set_threads(int n);
 
 /* synthetic-workload twin of the product's on-device generator (oracle/synth_oracle.c) */
 void oracle_synth_dense_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, float *X);
+void oracle_synth_dense_f32_placed(uint64_t seed, int64_t row0, int64_t rows, int32_t d, float *X, int partitions,
+                                   int threads);
 void oracle_synth_wtrue(uint64_t seed, int32_t d, double *w);
 void oracle_synth_labels(uint64_t seed, int kind, int64_t row0, int64_t rows, int32_t d, const float *X,
                          const double *w_true, double *labels);

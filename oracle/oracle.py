@@ -226,3 +226,38 @@ def synth_csr_f32(seed: int, row0: int, rows: int, d: int, k: int):
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+def host_threads() -> int:
+    """CPUs this process may run on (not OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def bind_threads(threads: int) -> int:
+    """Pins OpenMP thread t to the t-th CPU of the affinity mask (CPU-timing hygiene; see agd_oracle.c)."""
+    lib().oracle_set_threads(C.c_int(threads))
+    lib().oracle_bind_threads.restype = C.c_int
+    return lib().oracle_bind_threads(C.c_int(threads))
+
+
+def unbind_threads() -> None:
+    lib().oracle_unbind_threads()
+
+
+def first_touch(a: np.ndarray, partitions: int, threads: int) -> np.ndarray:
+    """Zero-fills a fresh (rows, ...) array partition by partition in oracle_smooth's thread mapping."""
+    rows = a.shape[0]
+    lib().oracle_first_touch(_p(a), C.c_int64(rows), C.c_int64(a.nbytes // max(rows, 1)), C.c_int(partitions),
+                             C.c_int(threads))
+    return a
+
+
+def synth_dense_f32_placed(seed: int, row0: int, rows: int, d: int, partitions: int, threads: int) -> np.ndarray:
+    """synth_dense_f32 written partition by partition by the threads that will fold those partitions."""
+    X = np.empty((rows, d), dtype=np.float32)
+    lib().oracle_synth_dense_f32_placed(C.c_uint64(seed), C.c_int64(row0), C.c_int64(rows), C.c_int32(d), _p(X),
+                                        C.c_int(partitions), C.c_int(threads))
+    return X

@@ -50,21 +50,37 @@ static int32_t irwin_hall4(uint32_t a, uint32_t b) {
 
 static const double kScale64 = 1.7320508075688772 / 65536.0; /* sqrt(3)/65536 */
 
+static void synth_row_f32(uint32_t k0, uint32_t k1, float scale, uint64_t i, int32_t d, float *x) {
+  for (int32_t j = 0; j < d; j += 2) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)(j >> 1), 1u}, o[4];
+    philox4x32_10(k0, k1, c, o);
+    x[j] = (float)irwin_hall4(o[0], o[1]) * scale;
+    if (j + 1 < d) x[j + 1] = (float)irwin_hall4(o[2], o[3]) * scale;
+  }
+}
+
 void oracle_synth_dense_f32(uint64_t seed, int64_t row0, int64_t rows, int32_t d, float *X) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const float scale = (float)kScale64;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
-  for (int64_t r = 0; r < rows; ++r) {
-    const uint64_t i = (uint64_t)(row0 + r);
-    float *x = X + r * (int64_t)d;
-    for (int32_t j = 0; j < d; j += 2) {
-      uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)(j >> 1), 1u}, o[4];
-      philox4x32_10(k0, k1, c, o);
-      x[j] = (float)irwin_hall4(o[0], o[1]) * scale;
-      if (j + 1 < d) x[j + 1] = (float)irwin_hall4(o[2], o[3]) * scale;
-    }
+  for (int64_t r = 0; r < rows; ++r) synth_row_f32(k0, k1, scale, (uint64_t)(row0 + r), d, X + r * (int64_t)d);
+}
+
+/* Same values, written partition by partition in the thread mapping oracle_smooth folds them in (partition p on
+ * thread p % threads): on a NUMA host every page of X is first touched by the thread that will read it. */
+void oracle_synth_dense_f32_placed(uint64_t seed, int64_t row0, int64_t rows, int32_t d, float *X, int partitions,
+                                   int threads) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const float scale = (float)kScale64;
+  const int P = partitions < 1 ? 1 : partitions;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(threads > 0 ? threads : 1)
+#endif
+  for (int p = 0; p < P; ++p) {
+    const int64_t lo = (int64_t)(((__int128)p * rows) / P), hi = (int64_t)(((__int128)(p + 1) * rows) / P);
+    for (int64_t r = lo; r < hi; ++r) synth_row_f32(k0, k1, scale, (uint64_t)(row0 + r), d, X + r * (int64_t)d);
   }
 }
 

@@ -16,6 +16,8 @@ UPD_SIMPLE, UPD_SQUARED_L2, UPD_L1 = 0, 1, 2
 F64, F32, BF16 = 0, 1, 2
 FLAG_MEMOIZE_FX = 1
 FLAG_NO_FUSE = 2
+ABI_VERSION = 2
+XCHG_HANDLE_BYTES = 192
 
 
 class Params(C.Structure):
@@ -69,6 +71,10 @@ _SIGNATURES = {
     "agd_last_error": (C.c_char_p, [C.c_void_p]),
     "agd_comm_unique_id": (C.c_int, [C.c_void_p]),
     "agd_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "agd_comm_init_ipc": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "agd_xchg_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "agd_xchg_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "agd_kernel_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
     "agd_reserve": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32]),
     "agd_load_dense": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                  C.c_int32, C.c_int64, C.c_int32]),
@@ -120,7 +126,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError here means the .so does not export the ABI
             fn.restype = res
             fn.argtypes = args
-        if L.agd_abi_version() != 1:
+        if L.agd_abi_version() != ABI_VERSION:
             raise RuntimeError("libagd_b200.so ABI version mismatch")
         if L.agd_sizeof_params() != C.sizeof(Params) or L.agd_sizeof_stats() != C.sizeof(Stats):
             raise RuntimeError("agd_params / agd_stats layout differs between the binding and the library")

@@ -118,6 +118,8 @@ struct agd_handle {
   int32_t d_user = 0;  // the caller's feature count (what agd_dim reports)
   int world = 1, first_rank = 0;
   bool comm_ready = false;
+  bool comm_auto = false;   // the world is this process's own GPUs (agd_create): NCCL is only built if it is ever needed
+  bool ipc_only = false;    // agd_comm_init_ipc: no NCCL at all, the host ships the CUDA IPC handles (agd_xchg_export/import)
   int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised, 4 tcgen05 (bf16)
   int ring_stages = 0;
   int tune_rows = 0, tune_ctas = 0, tune_full = 0;
@@ -304,21 +306,48 @@ void free_xchg(agd_handle *h) {
   h->x_p2p = false;
 }
 
-// Builds the peer-memory exchange for the current dimension: every rank allocates xbuf/xflags, the CUDA IPC handles
-// travel once through an NCCL all-gather (setup only), remote ranks are mapped with cudaIpcOpenMemHandle and local
-// devices of this process with peer access.  Collective: every rank calls it from the same entry point.
-int ensure_xchg(agd_handle *h) {
-  if (h->world <= 1 || h->collective == 1) return 0;
-  if (h->x_d == h->d) return 0;
-  free_xchg(h);
-  h->x_d = h->d;
-  const int W = h->world, nd = (int)h->devs.size();
-  if (W > kMaxRanks) { if (h->collective == 2) return fail(h, "peer exchange supports at most %d ranks", kMaxRanks); return 0; }
+// What one rank tells the others about its exchange buffers (AGD_XCHG_HANDLE_BYTES on the wire).
+struct XHandles {
+  cudaIpcMemHandle_t buf, flags;
+  int32_t can_peer, d, rank, pad;
+  unsigned char reserve[AGD_XCHG_HANDLE_BYTES - 2 * sizeof(cudaIpcMemHandle_t) - 16];
+};
+static_assert(sizeof(XHandles) == AGD_XCHG_HANDLE_BYTES, "exchange handle blob size is part of the ABI");
+
+void destroy_comms(agd_handle *h) {
+  for (Dev &D : h->devs) {
+    if (D.comm && nccl_api().ok) { cudaSetDevice(D.ordinal); nccl_api().CommDestroy(D.comm); }
+    D.comm = nullptr;
+  }
+}
+
+// NCCL communicator of a single-process world, built on first need (fallback / collective=nccl)
+int ensure_nccl(agd_handle *h) {
+  if (h->world <= 1) return 0;
+  bool have = true;
+  for (Dev &D : h->devs) have = have && D.comm != nullptr;
+  if (have) return 0;
+  if (h->ipc_only) return fail(h, "this world was set up with agd_comm_init_ipc: there is no NCCL communicator to fall back to");
+  if (!h->comm_auto) return fail(h, "world_ranks=%d but agd_comm_init was not called", h->world);
   NcclApi &N = nccl_api();
+  if (!N.ok) return fail(h, "NCCL unavailable: %s", N.why.c_str());
+  ncclUniqueId id;
+  CKN(N.GetUniqueId(&id));
+  const int nd = (int)h->devs.size();
+  CKN(N.GroupStart());
+  for (int i = 0; i < nd; ++i) {
+    CK(cudaSetDevice(h->devs[i].ordinal));
+    CKN(N.CommInitRank(&h->devs[i].comm, nd, id, i));
+  }
+  CKN(N.GroupEnd());
+  return 0;
+}
+
+// step 1 of the exchange setup: allocate this process's buffers for the current dimension and describe them
+int xchg_alloc(agd_handle *h, std::vector<XHandles> &mine) {
+  const int W = h->world, nd = (int)h->devs.size();
   const size_t n = (size_t)h->d + 4;
-  struct Handles { cudaIpcMemHandle_t buf, flags; int can_peer; int pad[3]; };
-  std::vector<Handles> mine(nd), all((size_t)W);
-  // 1. allocate + export
+  mine.assign((size_t)nd, XHandles());
   for (int i = 0; i < nd; ++i) {
     Dev &D = h->devs[i];
     CK(cudaSetDevice(D.ordinal));
@@ -328,8 +357,10 @@ int ensure_xchg(agd_handle *h) {
     CK(cudaMemset(D.xbuf, 0, 2 * (size_t)W * n * sizeof(double)));
     CK(cudaMemset(D.xflags, 0, 2 * (size_t)W * sizeof(unsigned long long)));
     CK(cudaMemset(D.xticket, 0, sizeof(unsigned int)));
-    memset(&mine[i], 0, sizeof(Handles));
+    memset(&mine[i], 0, sizeof(XHandles));
     mine[i].can_peer = 1;
+    mine[i].d = h->d;
+    mine[i].rank = h->first_rank + i;
     for (int j = 0; j < nd; ++j) {
       if (j == i) continue;
       int can = 0;
@@ -337,34 +368,21 @@ int ensure_xchg(agd_handle *h) {
       if (!can) mine[i].can_peer = 0;
       else { cudaError_t e = cudaDeviceEnablePeerAccess(h->devs[j].ordinal, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) mine[i].can_peer = 0; cudaGetLastError(); }
     }
-    if (cudaIpcGetMemHandle(&mine[i].buf, D.xbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine[i].flags, D.xflags) != cudaSuccess) {
-      mine[i].can_peer = 0;
-      cudaGetLastError();
+    if (nd < W) {  // buffers of other processes are reached through CUDA IPC
+      if (cudaIpcGetMemHandle(&mine[i].buf, D.xbuf) != cudaSuccess || cudaIpcGetMemHandle(&mine[i].flags, D.xflags) != cudaSuccess) {
+        mine[i].can_peer = 0;
+        cudaGetLastError();
+      }
     }
   }
-  // 2. all-gather the handles (device staging through NCCL; setup only)
-  {
-    std::vector<void *> stage(nd);
-    for (int i = 0; i < nd; ++i) {
-      Dev &D = h->devs[i];
-      CK(cudaSetDevice(D.ordinal));
-      CK(cudaMalloc(&stage[i], (size_t)W * sizeof(Handles)));
-      CK(cudaMemcpyAsync((char *)stage[i] + (size_t)(h->first_rank + i) * sizeof(Handles), &mine[i], sizeof(Handles), cudaMemcpyHostToDevice, D.st));
-    }
-    CKN(N.GroupStart());
-    for (int i = 0; i < nd; ++i) {
-      Dev &D = h->devs[i];
-      CKN(N.AllGather((char *)stage[i] + (size_t)(h->first_rank + i) * sizeof(Handles), stage[i], sizeof(Handles), ncclChar, D.comm, D.st));
-    }
-    CKN(N.GroupEnd());
-    CK(cudaSetDevice(h->devs[0].ordinal));
-    CK(cudaMemcpyAsync(all.data(), stage[0], (size_t)W * sizeof(Handles), cudaMemcpyDeviceToHost, h->devs[0].st));
-    for (int i = 0; i < nd; ++i) { CK(cudaSetDevice(h->devs[i].ordinal)); CK(cudaStreamSynchronize(h->devs[i].st)); }
-    for (int i = 0; i < nd; ++i) { cudaSetDevice(h->devs[i].ordinal); cudaFree(stage[i]); }
-  }
+  return 0;
+}
+
+// step 3: map every rank's buffers into every local device; *ok_out = false when some pair cannot be mapped
+int xchg_map(agd_handle *h, const std::vector<XHandles> &all, bool *ok_out) {
+  const int W = h->world, nd = (int)h->devs.size();
   bool ok = true;
-  for (int r = 0; r < W; ++r) ok = ok && all[r].can_peer;
-  // 3. map every rank's buffers into every local device
+  for (int r = 0; r < W; ++r) ok = ok && all[(size_t)r].can_peer && all[(size_t)r].d == h->d && all[(size_t)r].rank == r;
   for (int i = 0; i < nd && ok; ++i) {
     Dev &D = h->devs[i];
     CK(cudaSetDevice(D.ordinal));
@@ -376,8 +394,8 @@ int ensure_xchg(agd_handle *h) {
         continue;
       }
       void *pb = nullptr, *pf = nullptr;
-      if (cudaIpcOpenMemHandle(&pb, all[r].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-          cudaIpcOpenMemHandle(&pf, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      if (cudaIpcOpenMemHandle(&pb, all[(size_t)r].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, all[(size_t)r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
         ok = false;
         break;
@@ -388,12 +406,55 @@ int ensure_xchg(agd_handle *h) {
       D.xpeers.flag[r] = (unsigned long long *)pf;
     }
   }
-  // every rank must take the same decision: agree through one more (tiny) all-reduce of the ok flag
-  {
-    int *flagdev = nullptr;
-    Dev &D0 = h->devs[0];
-    CK(cudaSetDevice(D0.ordinal));
-    CK(cudaMalloc(&flagdev, sizeof(int) * nd));
+  *ok_out = ok;
+  return 0;
+}
+
+// Builds the peer-memory exchange for the current dimension.  Three transports for the setup (never for the data):
+//  * every rank is a GPU of this process: nothing travels (direct peer pointers), NCCL is not touched;
+//  * agd_comm_init worlds: the CUDA IPC handles travel once through an NCCL all-gather, the yes/no decision through a
+//    one-int all-reduce; if some pair of ranks cannot map each other NCCL carries the all-reduce instead;
+//  * agd_comm_init_ipc worlds: the host ships the handles (agd_xchg_export / agd_xchg_import) -- no NCCL anywhere.
+// Collective: every rank calls it from the same entry point.
+int ensure_xchg(agd_handle *h) {
+  if (h->world <= 1) return 0;
+  if (h->collective == 1) return ensure_nccl(h);
+  if (h->x_d == h->d) return h->x_p2p ? 0 : ensure_nccl(h);
+  if (h->ipc_only)
+    return fail(h, "peer-memory exchange not established for d=%d: call agd_xchg_export / agd_xchg_import after loading the shards", h->d);
+  free_xchg(h);
+  h->x_d = h->d;
+  const int W = h->world, nd = (int)h->devs.size();
+  if (W > kMaxRanks) { if (h->collective == 2) return fail(h, "peer exchange supports at most %d ranks", kMaxRanks); return ensure_nccl(h); }
+  std::vector<XHandles> mine, all((size_t)W);
+  if (xchg_alloc(h, mine)) return 1;
+  bool ok = true;
+  if (nd == W) {
+    all = mine;
+    if (xchg_map(h, all, &ok)) return 1;
+  } else {
+    if (ensure_nccl(h)) return 1;
+    NcclApi &N = nccl_api();
+    // all-gather the handles (device staging through NCCL; setup only)
+    std::vector<void *> stage(nd);
+    for (int i = 0; i < nd; ++i) {
+      Dev &D = h->devs[i];
+      CK(cudaSetDevice(D.ordinal));
+      CK(cudaMalloc(&stage[i], (size_t)W * sizeof(XHandles)));
+      CK(cudaMemcpyAsync((char *)stage[i] + (size_t)(h->first_rank + i) * sizeof(XHandles), &mine[i], sizeof(XHandles), cudaMemcpyHostToDevice, D.st));
+    }
+    CKN(N.GroupStart());
+    for (int i = 0; i < nd; ++i) {
+      Dev &D = h->devs[i];
+      CKN(N.AllGather((char *)stage[i] + (size_t)(h->first_rank + i) * sizeof(XHandles), stage[i], sizeof(XHandles), ncclChar, D.comm, D.st));
+    }
+    CKN(N.GroupEnd());
+    CK(cudaSetDevice(h->devs[0].ordinal));
+    CK(cudaMemcpyAsync(all.data(), stage[0], (size_t)W * sizeof(XHandles), cudaMemcpyDeviceToHost, h->devs[0].st));
+    for (int i = 0; i < nd; ++i) { CK(cudaSetDevice(h->devs[i].ordinal)); CK(cudaStreamSynchronize(h->devs[i].st)); }
+    for (int i = 0; i < nd; ++i) { cudaSetDevice(h->devs[i].ordinal); cudaFree(stage[i]); }
+    if (xchg_map(h, all, &ok)) return 1;
+    // every rank must take the same decision: agree through one more (tiny) all-reduce of the ok flag
     int v = ok ? 1 : 0;
     std::vector<int *> fl(nd);
     for (int i = 0; i < nd; ++i) {
@@ -404,11 +465,9 @@ int ensure_xchg(agd_handle *h) {
     CKN(N.GroupStart());
     for (int i = 0; i < nd; ++i) CKN(N.AllReduce(fl[i], fl[i], 1, ncclInt, ncclMin, h->devs[i].comm, h->devs[i].st));
     CKN(N.GroupEnd());
-    CK(cudaSetDevice(D0.ordinal));
-    CK(cudaMemcpyAsync(&v, fl[0], sizeof(int), cudaMemcpyDeviceToHost, D0.st));
+    CK(cudaSetDevice(h->devs[0].ordinal));
+    CK(cudaMemcpyAsync(&v, fl[0], sizeof(int), cudaMemcpyDeviceToHost, h->devs[0].st));
     for (int i = 0; i < nd; ++i) { CK(cudaSetDevice(h->devs[i].ordinal)); CK(cudaStreamSynchronize(h->devs[i].st)); cudaFree(fl[i]); }
-    cudaSetDevice(D0.ordinal);
-    cudaFree(flagdev);
     ok = v == 1;
   }
   if (!ok) {
@@ -416,7 +475,7 @@ int ensure_xchg(agd_handle *h) {
     const int32_t keep = h->x_d;
     free_xchg(h);
     h->x_d = keep;  // do not retry every pass; NCCL carries the all-reduce
-    return 0;
+    return ensure_nccl(h);
   }
   h->x_p2p = true;
   h->x_epoch = 0;
@@ -520,7 +579,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     h->launches += 1;
     h->collectives += 1;
   } else if (h->world > 1) {
-    if (!h->comm_ready) return fail(h, "world_ranks=%d but agd_comm_init was not called", h->world);
+    if (!h->comm_ready || !h->devs[0].comm) return fail(h, "world_ranks=%d but there is no communicator (agd_comm_init)", h->world);
     NcclApi &N = nccl_api();
     Dev &D0 = h->devs[0];
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
@@ -602,6 +661,10 @@ double reg_value(int updater, double reg, double sum_sq, double sum_abs) {
 
 }  // namespace
 
+namespace agd {
+void set_last_error(agd_handle *h, const char *msg) { fail(h, "%s", msg); }
+}  // namespace agd
+
 // ================================================================ C-ABI
 extern "C" {
 
@@ -667,15 +730,11 @@ int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
   nh->first_rank = 0;
   for (int i = 0; i < n_dev; ++i) nh->devs[i].row_base = (long long)i << 40;  // loaded shards: one mask stream per rank
   *out = nh;
-  if (n_dev > 1) {  // single-process owner of several GPUs: build the communicator now
-    unsigned char id[128];
-    if (agd_comm_unique_id(id) || agd_comm_init(nh, id, n_dev, 0)) {
-      fail(h, "communicator setup failed: %s", nh->err.c_str());
-      *out = nullptr;
-      agd_destroy(nh);
-      return 1;
-    }
-  }
+  // A single-process owner of several GPUs is a complete world of its own: ranks 0..n_dev-1 exchange through direct peer
+  // pointers, and NCCL is built only if it is ever needed (ensure_nccl).  agd_comm_init / agd_comm_init_ipc replace this
+  // default when the process is part of a larger world.
+  nh->comm_auto = true;
+  nh->comm_ready = true;
   return 0;
 }
 
@@ -686,6 +745,7 @@ int agd_destroy(agd_handle *h) {
     cudaSetDevice(D.ordinal);
     cudaStreamSynchronize(D.st);
     if (D.comm && nccl_api().ok) nccl_api().CommDestroy(D.comm);
+    D.comm = nullptr;
     free_shard(h, D);
     double *v[] = {D.x, D.z, D.x_old, D.z_old, D.y, D.g_y, D.g_x, D.wtmp, D.acc, D.slabs, D.partials};
     for (double *p : v)
@@ -723,7 +783,12 @@ int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t
   const int nd = (int)h->devs.size();
   if (world_ranks < nd || first_rank < 0 || first_rank + nd > world_ranks)
     return fail(h, "bad rank layout: world=%d first=%d local=%d", world_ranks, first_rank, nd);
-  if (h->comm_ready) return fail(h, "communicator already initialised");
+  if (h->comm_ready && !h->comm_auto) return fail(h, "communicator already initialised");
+  // replaces the default single-process world of agd_create (its NCCL communicator, if one was ever built, and its exchange)
+  free_xchg(h);
+  destroy_comms(h);
+  h->comm_auto = false;
+  h->ipc_only = false;
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   if (world_ranks > 1) {
@@ -738,6 +803,60 @@ int agd_comm_init(agd_handle *h, const void *id128, int32_t world_ranks, int32_t
   h->first_rank = first_rank;
   h->comm_ready = true;
   for (int i = 0; i < nd; ++i) h->devs[i].row_base = (long long)(first_rank + i) << 40;
+  return 0;
+}
+
+// ---- the same world without NCCL: the host language ships the CUDA IPC handles of the exchange buffers
+int agd_comm_init_ipc(agd_handle *h, int32_t world_ranks, int32_t first_rank) {
+  if (!h) return 1;
+  const int nd = (int)h->devs.size();
+  if (world_ranks < nd || first_rank < 0 || first_rank + nd > world_ranks)
+    return fail(h, "bad rank layout: world=%d first=%d local=%d", world_ranks, first_rank, nd);
+  if (world_ranks > kMaxRanks) return fail(h, "the peer-memory exchange supports at most %d ranks", kMaxRanks);
+  if (h->comm_ready && !h->comm_auto) return fail(h, "communicator already initialised");
+  free_xchg(h);
+  destroy_comms(h);
+  h->comm_auto = false;
+  h->ipc_only = world_ranks > nd;   // a world of local GPUs only needs no handles at all
+  if (!h->ipc_only) h->comm_auto = true;
+  h->world = world_ranks;
+  h->first_rank = first_rank;
+  h->comm_ready = true;
+  for (int i = 0; i < nd; ++i) h->devs[i].row_base = (long long)(first_rank + i) << 40;
+  return 0;
+}
+
+int agd_xchg_export(agd_handle *h, void *out, int64_t capacity_bytes, int64_t *bytes_written) {
+  if (!h || !out || !bytes_written) return 1;
+  if (!h->ipc_only) return fail(h, "agd_xchg_export needs a world set up with agd_comm_init_ipc");
+  if (h->d <= 0) return fail(h, "load the shards first: the exchange buffers are sized by the feature dimension");
+  const int nd = (int)h->devs.size();
+  if (capacity_bytes < (int64_t)nd * AGD_XCHG_HANDLE_BYTES) return fail(h, "capacity too small: need %d bytes", nd * AGD_XCHG_HANDLE_BYTES);
+  free_xchg(h);
+  std::vector<XHandles> mine;
+  if (xchg_alloc(h, mine)) return 1;
+  for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaDeviceSynchronize()); }  // the zeroed buffers are visible before any peer maps them
+  memcpy(out, mine.data(), (size_t)nd * sizeof(XHandles));
+  *bytes_written = (int64_t)nd * AGD_XCHG_HANDLE_BYTES;
+  return 0;
+}
+
+int agd_xchg_import(agd_handle *h, const void *all_ranks, int64_t bytes) {
+  if (!h || !all_ranks) return 1;
+  if (!h->ipc_only) return fail(h, "agd_xchg_import needs a world set up with agd_comm_init_ipc");
+  if (!h->devs[0].xbuf) return fail(h, "call agd_xchg_export first");
+  if (bytes != (int64_t)h->world * AGD_XCHG_HANDLE_BYTES) return fail(h, "expected %d handle blobs (%d bytes)", h->world, h->world * AGD_XCHG_HANDLE_BYTES);
+  std::vector<XHandles> all((size_t)h->world);
+  memcpy(all.data(), all_ranks, (size_t)bytes);
+  bool ok = true;
+  if (xchg_map(h, all, &ok)) return 1;
+  if (!ok) {
+    free_xchg(h);
+    return fail(h, "peer-memory exchange unavailable: some pair of ranks cannot map each other's buffers (or the blobs are not in rank order / of another dimension)");
+  }
+  h->x_d = h->d;
+  h->x_p2p = true;
+  h->x_epoch = 0;
   return 0;
 }
 
@@ -847,8 +966,10 @@ int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_
   Dev &D = h->devs[dev];
   std::lock_guard<std::mutex> g(*D.mu);
   Shard &s = D.sh;
-  const int64_t nnz = rows > 0 ? rowptr[rows] - rowptr[0] : 0;
   if (rows > 0 && rowptr[0] != 0) return fail(h, "rowptr[0] must be 0");
+  const int64_t nnz = rows > 0 ? rowptr[rows] : 0;
+  if (nnz < 0) return fail(h, "rowptr[rows] = %lld is negative", (long long)nnz);
+  if (nnz > 0 && (!idx || !val)) return fail(h, "NULL index / value pointer");
   // APPENDS rows (Spark hands partitions over one at a time); arrays grow geometrically
   const int64_t need_rows = s.rows + rows, need_nnz = s.nnz + nnz;
   const int64_t rows_cap = need_rows > s.cap ? (need_rows > 2 * s.cap ? need_rows : 2 * s.cap) : s.cap;
@@ -870,6 +991,19 @@ int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_
       CK(cudaMemcpyAsync(stage_vals, val, (size_t)nnz * sb, cudaMemcpyHostToDevice, D.st));
       CK(convert_rows_launch((unsigned char *)s.val + (size_t)s.nnz * eb, eb, stage_vals, sb, nnz, 1, 1, 1, D.st));
     }
+  }
+  // Validate on the device before the partition becomes part of the shard: the gradient kernel gathers w[idx] and
+  // scatters into g[idx] with these raw indices, so one bad column id would be an out-of-bounds device write.
+  if (rows > 0) {
+    int *flag = nullptr, host_flag = 0;   // D.stage_dev still holds the caller's rowptr
+    CK(cudaMalloc(&flag, sizeof(int)));
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), D.st));
+    CK(csr_validate_launch((const int64_t *)D.stage_dev, rows, s.idx + s.nnz, nnz, d, flag, D.st));
+    CK(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, D.st));
+    CK(cudaStreamSynchronize(D.st));
+    cudaFree(flag);
+    if (host_flag == 1) return fail(h, "bad CSR partition: rowptr must be non-decreasing from 0 to nnz=%lld", (long long)nnz);
+    if (host_flag == 2) return fail(h, "bad CSR partition: a column index lies outside [0, %d) (SparseVector size differs from the weights?)", d);
   }
   CK(cudaStreamSynchronize(D.st));
   s.rows = need_rows;
@@ -1000,6 +1134,21 @@ int agd_synth_wtrue(agd_handle *h, uint64_t seed, int32_t d, double *w_out) {
   CK(cudaStreamSynchronize(D.st));
   cudaFree(tmp);
   return 0;
+}
+
+const char *agd_kernel_name(const agd_handle *h, int32_t dev) {
+  if (!h || dev < 0 || dev >= (int)h->devs.size() || h->d <= 0) return "";
+  const Shard &s = h->devs[dev].sh;
+  if (s.csr) return s.elem_bytes == 8 ? "k1_csr_kernel<double>" : "k1_csr_kernel<float>";
+  const int eb = s.elem_bytes ? s.elem_bytes : 4;
+  const char *t = eb == 8 ? "double" : (eb == 4 ? "float" : "__nv_bfloat16");
+  static thread_local char buf[96];
+  switch (dense_kernel_of(h, eb)) {
+    case 3: return "k1_tc_kernel (tcgen05, bf16 storage)";
+    case 2: snprintf(buf, sizeof buf, "k1_ws_kernel<%s,...>", t); return buf;
+    case 1: snprintf(buf, sizeof buf, "k1_ring_kernel<%s,...>", t); return buf;
+    default: snprintf(buf, sizeof buf, "k1_generic_kernel<%s>", t); return buf;
+  }
 }
 
 int agd_set_option(agd_handle *h, const char *key, const char *value) {

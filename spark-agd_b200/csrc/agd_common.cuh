@@ -146,6 +146,14 @@ cudaError_t synth_csr_launch(int64_t *rowptr, int32_t *idx, void *val, int elem_
 // dst[i] = src[i] + shift (rebasing an appended partition's rowptr onto the resident CSR shard)
 cudaError_t csr_shift_rowptr_launch(int64_t *dst, const int64_t *src, int64_t n, int64_t shift, cudaStream_t st);
 
+// rowptr (as the caller passed it: rows + 1 entries from 0) and idx of an appended CSR partition, checked on the device:
+// *flag = 0 ok, 1 = rowptr not monotone / not ending at nnz, 2 = a column id outside [0, d)
+cudaError_t csr_validate_launch(const int64_t *rowptr_host_order, int64_t rows, const int32_t *idx, int64_t nnz, int32_t d,
+                                int *flag, cudaStream_t st);
+
+// records `msg` as the handle's agd_last_error (for translation units other than agd_api.cu)
+void set_last_error(agd_handle *h, const char *msg);
+
 // ---------------------------------------------------------------- load path
 // dst (store dtype, rows x dst_ld, columns >= d zero) <- src (src dtype, leading dimension ld), rows x d
 cudaError_t convert_rows_launch(void *dst, int dst_bytes, const void *src, int src_bytes, int64_t rows, int32_t d,

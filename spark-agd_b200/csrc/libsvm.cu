@@ -12,7 +12,11 @@
 #include <string>
 #include <vector>
 
+#include <limits.h>
+
 #include "../../include/agd_b200.h"
+
+namespace agd { void set_last_error(agd_handle *h, const char *msg); }  // agd_api.cu (internal, not part of the ABI)
 
 extern "C" {
 
@@ -58,6 +62,10 @@ int agd_libsvm_read(const char *path, int32_t num_features, agd_libsvm **out) {
       const double v = strtod(p, &q);
       if (q == p) { L->err = "line " + std::to_string(lineno) + ": cannot parse a value"; fclose(f); free(line); return 1; }
       p = q;
+      if (index > (long)INT32_MAX) {  // must be rejected BEFORE the narrowing cast below
+        L->err = "line " + std::to_string(lineno) + ": feature index " + std::to_string(index) + " exceeds the int32 range";
+        fclose(f); free(line); return 1;
+      }
       if (index < 1 || index <= prev) {  // loadLibSVMFile requires one-based ascending indices
         L->err = "line " + std::to_string(lineno) + ": indices must be one-based and ascending";
         fclose(f); free(line); return 1;
@@ -92,11 +100,12 @@ void agd_libsvm_free(agd_libsvm *L) { delete L; }
 
 // Parse + shard: rows are split contiguously over the handle's local GPUs (CSR storage `store_dtype`).
 int agd_load_libsvm(agd_handle *h, const char *path, int32_t num_features, int32_t store_dtype) {
+  if (!h) return 1;
   agd_libsvm *L = nullptr;
   int rc = agd_libsvm_read(path, num_features, &L);
   if (rc) {
-    // surface the parser's message through a failing load on the handle
-    fprintf(stderr, "agd_load_libsvm: %s\n", agd_libsvm_error(L));
+    // the parser's message becomes the handle's agd_last_error (what MLUtils.loadLibSVMFile's caller sees as the exception text)
+    agd::set_last_error(h, (std::string("agd_load_libsvm: ") + agd_libsvm_error(L)).c_str());
     agd_libsvm_free(L);
     return 1;
   }

@@ -177,6 +177,18 @@ __global__ void csr_shift_rowptr_kernel(long long *dst, const long long *src, lo
   for (long long q = blockIdx.x * 256LL + threadIdx.x; q < n; q += (long long)gridDim.x * 256LL) dst[q] = src[q] + shift;
 }
 
+// Validates an appended CSR partition on the device (the host never scans the index stream): rowptr[0..rows] must be
+// non-decreasing, start at 0 and stay within nnz; every column id must lie in [0, d).  flag: 0 ok, 1 rowptr, 2 column.
+__global__ void csr_validate_kernel(const long long *rowptr, long long rows, const int *idx, long long nnz, int d, int *flag) {
+  const long long stride = (long long)gridDim.x * 256LL;
+  for (long long q = blockIdx.x * 256LL + threadIdx.x; q <= rows; q += stride) {
+    const long long v = rowptr[q];
+    if (v < 0 || v > nnz || (q == 0 && v != 0) || (q == rows && v != nnz) || (q < rows && rowptr[q + 1] < v)) atomicMax(flag, 1);
+  }
+  for (long long q = blockIdx.x * 256LL + threadIdx.x; q < nnz; q += stride)
+    if ((unsigned)idx[q] >= (unsigned)d) atomicMax(flag, 2);
+}
+
 inline unsigned grid_for(long long total) {
   long long g = (total + 255) / 256;
   if (g > 148LL * 16) g = 148LL * 16;
@@ -220,6 +232,13 @@ cudaError_t synth_labels_launch(const void *X, int elem_bytes, const double *w_t
 cudaError_t csr_shift_rowptr_launch(int64_t *dst, const int64_t *src, int64_t n, int64_t shift, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   csr_shift_rowptr_kernel<<<grid_for(n), 256, 0, st>>>((long long *)dst, (const long long *)src, n, shift);
+  return cudaGetLastError();
+}
+
+cudaError_t csr_validate_launch(const int64_t *rowptr_host_order, int64_t rows, const int32_t *idx, int64_t nnz, int32_t d,
+                                int *flag, cudaStream_t st) {
+  csr_validate_kernel<<<grid_for(nnz > rows ? nnz : rows + 1), 256, 0, st>>>((const long long *)rowptr_host_order, rows, idx,
+                                                                              nnz, d, flag);
   return cudaGetLastError();
 }
 

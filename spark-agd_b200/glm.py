@@ -98,9 +98,13 @@ class GeneralizedLinearAlgorithm:
     def run(self, sc: Context, labels, X, initialWeights=None):
         Xt, scale = self.prepare(X)
         d = np.asarray(X).shape[1]
-        w0 = np.zeros(Xt.shape[1]) if initialWeights is None else np.asarray(initialWeights, dtype=np.float64)
-        if initialWeights is not None and self.addIntercept and w0.shape[0] == d:
-            w0 = np.concatenate([w0, [0.0]])
+        # GeneralizedLinearAlgorithm.run [mllib-1.3.0]: initialWeights default to zeros(numFeatures), and with addIntercept
+        # the optimizer starts from appendBias(initialWeights) -- i.e. the initial INTERCEPT is 1.0, not 0.0
+        w0 = np.zeros(d) if initialWeights is None else np.asarray(initialWeights, dtype=np.float64)
+        if w0.ndim != 1 or w0.shape[0] != d:
+            raise ValueError(f"initialWeights has size {w0.shape}, data has {d} features")
+        if self.addIntercept:
+            w0 = np.concatenate([w0, [1.0]])
         data = sc.parallelize(labels, Xt, store=self.store).cache()
         try:
             w = self.optimizer.optimize(data, w0)

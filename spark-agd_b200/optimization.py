@@ -96,22 +96,33 @@ def _ptr(a):
 class Context:
     """Which local GPUs this process drives and how its ranks sit in the world (one rank per GPU).
 
-    devices: local CUDA ordinals.  world_size/first_rank: global layout; id_exchange(bytes|None) ->
-    bytes must return rank 0's 128-byte NCCL id on every process (e.g. a torch.distributed
-    broadcast) and is only needed when world_size > len(devices)."""
+    devices: local CUDA ordinals.  world_size/first_rank: global layout.  Multi-process worlds
+    (world_size > len(devices)) pick how the exchange is SET UP (the per-pass data never touches a library):
+      transport="nccl": id_exchange(bytes|None) -> bytes returns rank 0's 128-byte NCCL id on every process
+                        (e.g. a torch.distributed broadcast); NCCL ships the CUDA IPC handles and is the fallback;
+      transport="ipc":  handle_exchange(bytes) -> bytes returns every process's handle blob concatenated in rank
+                        order (an all-gather in the host language); no NCCL anywhere -- also works for several
+                        processes sharing one GPU."""
 
     def __init__(self, devices: Sequence[int] = (0,), world_size: Optional[int] = None, first_rank: int = 0,
-                 id_exchange=None):
+                 id_exchange=None, handle_exchange=None, transport: Optional[str] = None):
         self.devices = list(devices)
         self.world_size = len(self.devices) if world_size is None else int(world_size)
         self.first_rank = int(first_rank)
         self.id_exchange = id_exchange
-        if self.world_size > len(self.devices) and id_exchange is None:
-            raise ValueError("multi-process worlds need id_exchange to ship the NCCL unique id")
+        self.handle_exchange = handle_exchange
+        self.transport = transport or ("ipc" if (handle_exchange is not None and id_exchange is None) else "nccl")
+        if self.transport not in ("nccl", "ipc"):
+            raise ValueError("transport must be 'nccl' or 'ipc'")
+        if self.world_size > len(self.devices):
+            if self.transport == "nccl" and id_exchange is None:
+                raise ValueError("multi-process worlds need id_exchange to ship the NCCL unique id")
+            if self.transport == "ipc" and handle_exchange is None:
+                raise ValueError("transport='ipc' needs handle_exchange to ship the CUDA IPC handles")
 
     @staticmethod
-    def from_torch_distributed(local_device: Optional[int] = None) -> "Context":
-        """One process per GPU under torchrun: ranks/ids travel over the existing process group."""
+    def from_torch_distributed(local_device: Optional[int] = None, transport: str = "nccl") -> "Context":
+        """One process per GPU under torchrun: ranks/ids/handles travel over the existing process group."""
         import torch
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
@@ -122,14 +133,22 @@ class Context:
             dist.broadcast_object_list(buf, src=0)
             return buf[0]
 
-        return Context([dev], world_size=world, first_rank=rank, id_exchange=exchange)
+        def gather_handles(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return b"".join(out)
+
+        return Context([dev], world_size=world, first_rank=rank, id_exchange=exchange, handle_exchange=gather_handles,
+                       transport=transport)
 
     def _new_handle(self) -> C.c_void_p:
         L = N.lib()
         ids = (C.c_int32 * len(self.devices))(*self.devices)
         h = C.c_void_p()
         N.check(L.agd_create(ids, len(self.devices), C.byref(h)), None)
-        if self.world_size > len(self.devices):
+        if self.world_size > len(self.devices) and self.transport == "ipc":
+            N.check(L.agd_comm_init_ipc(h, self.world_size, self.first_rank), h)
+        elif self.world_size > len(self.devices):
             my_id = None
             if self.first_rank == 0:
                 buf = C.create_string_buffer(128)
@@ -176,6 +195,22 @@ class DeviceDataset:
         self.ctx = ctx
         self.h = ctx._new_handle()
         self.total_rows = 0
+        self._xchg_d = 0       # dimension the host-shipped exchange (transport="ipc") was set up for
+
+    def _ensure_exchange(self):
+        """transport="ipc": ship the CUDA IPC handles of the exchange buffers once per loaded dimension (collective:
+        every process reaches this from the same compute call)."""
+        c = self.ctx
+        if c.transport != "ipc" or c.world_size <= len(c.devices) or self._xchg_d == self.d:
+            return
+        L = N.lib()
+        cap = len(c.devices) * N.XCHG_HANDLE_BYTES
+        blob = C.create_string_buffer(cap)
+        n = C.c_int64()
+        N.check(L.agd_xchg_export(self.h, blob, cap, C.byref(n)), self.h)
+        everyone = c.handle_exchange(blob.raw[:n.value])
+        N.check(L.agd_xchg_import(self.h, C.c_char_p(everyone), len(everyone)), self.h)
+        self._xchg_d = self.d
 
     def cache(self) -> "DeviceDataset":  # shards are always resident; kept for call-site parity
         return self
@@ -184,6 +219,7 @@ class DeviceDataset:
         """Drops every shard but keeps the context (devices, communicator) for the next load."""
         N.check(N.lib().agd_clear(self.h), self.h)
         self.total_rows = 0
+        self._xchg_d = 0
         return self
 
     def load_dense(self, labels, X, store: str = "f64"):
@@ -237,6 +273,15 @@ class DeviceDataset:
         N.check(N.lib().agd_get_rows(self.h, dev, row0, rows, _ptr(X), _ptr(y)), self.h)
         return X, y
 
+    def get_labels(self, dev: int, row0: int, rows: int) -> np.ndarray:
+        y = np.empty(rows, dtype=np.float64)
+        N.check(N.lib().agd_get_rows(self.h, dev, row0, rows, None, _ptr(y)), self.h)
+        return y
+
+    def kernel_name(self, dev: int = 0) -> str:
+        """The gradient kernel this shard dispatches to (for reports)."""
+        return (N.lib().agd_kernel_name(self.h, dev) or b"").decode()
+
     def get_csr_rows(self, dev: int, row0: int, rows: int, nnz_capacity: int, dtype=np.float32):
         rowptr = np.empty(rows + 1, dtype=np.int64)
         idx = np.empty(nnz_capacity, dtype=np.int32)
@@ -258,6 +303,7 @@ class DeviceDataset:
             raise ValueError("weights have the wrong dimension")
         g = np.empty(self.d, dtype=np.float64)
         loss, cnt = C.c_double(), C.c_int64()
+        self._ensure_exchange()
         N.check(N.lib().agd_smooth(self.h, _grad_kind(gradient), _ptr(w), C.byref(loss), _ptr(g), C.byref(cnt)), self.h)
         return loss.value, g, cnt.value
 
@@ -270,6 +316,7 @@ class DeviceDataset:
             raise ValueError("weights have the wrong dimension")
         g = np.empty(self.d, dtype=np.float64)
         loss, loss2, cnt = C.c_double(), C.c_double(), C.c_int64()
+        self._ensure_exchange()
         N.check(N.lib().agd_smooth_pair(self.h, _grad_kind(gradient), _ptr(w), _ptr(w2), C.byref(loss), _ptr(g),
                                         C.byref(cnt), C.byref(loss2)), self.h)
         return loss.value, g, cnt.value, loss2.value
@@ -422,6 +469,7 @@ def run_with_stats(data: DeviceDataset, gradient, updater, convergenceTol, numIt
     w = np.empty_like(w0)
     hist = np.empty(max(int(numIterations), 1), dtype=np.float64)
     nh, st = C.c_int32(), N.Stats()
+    data._ensure_exchange()
     N.check(N.lib().agd_run(data.h, C.byref(p), _ptr(w0), _ptr(w), _ptr(hist), C.byref(nh), C.byref(st)), data.h)
     return w, hist[:nh.value].copy(), _stats(st)
 
@@ -433,10 +481,15 @@ class GradientDescent:
     @staticmethod
     def runMiniBatchSGD(data: DeviceDataset, gradient: Gradient, updater: Updater, stepSize: float, numIterations: int,
                         regParam: float, miniBatchFraction: float, initialWeights):
+        if not isinstance(data, DeviceDataset):
+            raise TypeError("data must be a DeviceDataset (Context.parallelize(...)); there is no CPU path")
         w0 = np.ascontiguousarray(initialWeights, dtype=np.float64)
+        if w0.ndim != 1 or w0.shape[0] != data.d:   # the native side reads and writes agd_dim(h) doubles
+            raise ValueError(f"initialWeights has size {w0.shape}, data has {data.d} features")
         w = np.empty_like(w0)
         hist = np.empty(max(int(numIterations), 1), dtype=np.float64)
         nh, st = C.c_int32(), N.Stats()
+        data._ensure_exchange()
         N.check(N.lib().agd_gd_run_minibatch(data.h, _grad_kind(gradient), _upd_kind(updater), stepSize,
                                              int(numIterations), regParam, float(miniBatchFraction), _ptr(w0), _ptr(w),
                                              _ptr(hist), C.byref(nh), C.byref(st)), data.h)

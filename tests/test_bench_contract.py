@@ -37,6 +37,15 @@ def test_reference_arm_is_silent_on_other_ranks():
                      env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
 
 
+def test_reference_arm_uses_every_host_thread_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must still use the host's cores."""
+    lines = run_bench("--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--cpu-rows", "20000",
+                      env={"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0", "OMP_NUM_THREADS": "1"})
+    assert len(lines) == 1
+    cb = json.loads(lines[0])["cpu_baseline"]
+    assert cb["cores"] == len(os.sched_getaffinity(0)) and len(cb["runs_seconds"]) == 3
+
+
 @pytest.mark.gpu
 def test_b200_arm_prints_the_contract_line():
     lines = run_bench("--rows", "400000", "--steps", "4", "--warmup", "3", "--cpu-rows", "20000")
@@ -56,3 +65,8 @@ def test_b200_arm_prints_the_contract_line():
     assert j["sweeps"] >= j["passes"] - j["fused_passes"] and j["fused_passes"] == 3
     assert j["unfused"]["loss_history_bit_identical_to_fused"] is True and j["unfused"]["sweeps"] == j["passes"]
     assert j["clocks"] is None or {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"])
+    # the full-workload comparison with the oracle rides in the line itself (north_star: weights within 1e-5)
+    p = j["parity"]
+    assert p["rows"] == 400000 and p["iters"] == 10 and p["pass"] is True and p["shards_equal_cpu_twin"] is True
+    assert p["w_rel_err"] <= 1e-9 and p["max_loss_rel_err"] <= 1e-11 and p["passes_equal"] and p["history_len_equal"]
+    assert j["roofline"]["kernel"].startswith("k1_ring_kernel<float")

@@ -30,7 +30,8 @@ def test_logistic_regression_with_agd(agd, ctx, oracle):
     model = alg.run(ctx, y, X)
     # the same recipe with the oracle as the optimizer
     Xt, scale = alg.prepare(X)
-    ref = oracle.agd_run(oracle.Data(y, X=Xt), "logistic", "squared_l2", np.zeros(d + 1), convergence_tol=0.0,
+    w0 = np.concatenate([np.zeros(d), [1.0]])       # appendBias(initialWeights) [mllib-1.3.0]: the intercept starts at 1.0
+    ref = oracle.agd_run(oracle.Data(y, X=Xt), "logistic", "squared_l2", w0, convergence_tol=0.0,
                          num_iterations=40, reg_param=0.01)
     np.testing.assert_allclose(model.weights, ref.weights[:d] * scale, rtol=1e-7, atol=1e-10)
     np.testing.assert_allclose(model.intercept, ref.weights[-1], rtol=1e-7)

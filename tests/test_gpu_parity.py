@@ -631,7 +631,30 @@ def test_argument_errors(agd, ctx):
         agd.AcceleratedGradientDescent(agd.LogisticGradient(), agd.SimpleUpdater()).optimize(data, [1.0, 2.0])
     with pytest.raises(agd.NativeError, match="dimension mismatch"):
         data.load_dense(np.ones(2), np.ones((2, 5)))
+    with pytest.raises(ValueError):          # the native side reads / writes agd_dim doubles through these buffers
+        agd.GradientDescent.runMiniBatchSGD(data, agd.LogisticGradient(), agd.SimpleUpdater(), 1.0, 2, 0.0, 1.0, [1.0, 2.0])
     data.close()
+
+
+def test_bad_csr_partitions_are_rejected_at_load(agd, ctx):
+    """The gradient kernel gathers w[idx] and scatters into g[idx]: a column id outside [0, d), or a SparseVector whose size
+    differs from the weights', must fail at load -- not corrupt neighbouring device allocations."""
+    y = np.array([1.0, 0.0, 1.0])
+    good = (np.array([0, 2, 3, 5]), np.array([0, 4, 2, 1, 3], dtype=np.int32), np.ones(5))
+    ds = ctx.parallelize_csr(y, *good, d=5)
+    l0, g0, c0 = ds.smooth(agd.HingeGradient(), np.zeros(5))
+    for rowptr, idx, msg in [
+        (np.array([0, 2, 3, 5]), np.array([0, 5, 2, 1, 3], dtype=np.int32), "column index"),      # idx == d
+        (np.array([0, 2, 3, 5]), np.array([0, -1, 2, 1, 3], dtype=np.int32), "column index"),     # negative
+        (np.array([0, 3, 2, 5]), np.array([0, 4, 2, 1, 3], dtype=np.int32), "rowptr"),            # not monotone
+    ]:
+        with pytest.raises(agd.NativeError, match=msg):
+            ds.load_csr(y, rowptr, idx, np.ones(5), 5)
+    # nothing of the rejected partitions became part of the shard
+    assert ds.local_rows(0) == 3
+    l1, g1, c1 = ds.smooth(agd.HingeGradient(), np.zeros(5))
+    assert (l1, c1) == (l0, c0) and np.array_equal(g0, g1)
+    ds.close()
 
 
 # ------------------------------------------------------------------ synthetic generator vs its CPU twin
@@ -689,6 +712,30 @@ def test_full_size_properties(agd, ctx, oracle):
 
 
 # ------------------------------------------------------------------ several GPUs in one process
+def test_local_world_can_be_replaced_by_a_larger_one(agd):
+    """agd_create makes the local GPUs a complete world; agd_comm_init on the same handle must be able to replace it with
+    `first_rank .. first_rank + n_dev - 1 of a larger world` (include/agd_b200.h; ADVICE r1: it used to be rejected)."""
+    import ctypes as C
+    import torch
+    N = agd._native
+    L = N.lib()
+    nd = min(torch.cuda.device_count(), 2)
+    ids = (C.c_int32 * nd)(*range(nd))
+    h = C.c_void_p()
+    N.check(L.agd_create(ids, nd, C.byref(h)), None)
+    buf = C.create_string_buffer(128)
+    N.check(L.agd_comm_unique_id(buf), None)
+    assert L.agd_comm_init(h, buf, nd, 0) == 0                      # replaces the default world (world == local GPUs here)
+    assert L.agd_comm_init(h, buf, nd, 0) != 0                      # ... once
+    assert b"already initialised" in L.agd_last_error(h)
+    L.agd_destroy(h)
+    h2 = C.c_void_p()
+    N.check(L.agd_create(ids, nd, C.byref(h2)), None)
+    assert L.agd_comm_init_ipc(h2, nd + 2, 1) == 0                  # ranks 1..nd of a world of nd + 2 processes' GPUs
+    assert L.agd_comm_init_ipc(h2, nd, nd) != 0 and b"bad rank layout" in L.agd_last_error(h2)
+    L.agd_destroy(h2)
+
+
 @pytest.mark.parametrize("collective", ["p2p", "nccl"])
 def test_two_local_gpus_match_one(agd, oracle, collective):
     import torch

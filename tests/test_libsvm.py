@@ -33,6 +33,21 @@ def test_parse_libsvm_rejects_bad_input(agd, tmp_path, bad):
         agd.MLUtils.parseLibSVMFile(str(tmp_path / "missing.libsvm"))
 
 
+def test_parse_libsvm_rejects_indices_beyond_int32(agd, tmp_path):
+    p = tmp_path / "big.libsvm"
+    p.write_text("1 1:1 4294967297:2\n")          # 2^32 + 1 would truncate to 1 and slip past the ordering check
+    with pytest.raises(ValueError, match="int32"):
+        agd.MLUtils.parseLibSVMFile(str(p))
+
+
+@pytest.mark.gpu
+def test_load_libsvm_reports_parse_errors_through_the_handle(agd, ctx, tmp_path):
+    p = tmp_path / "bad.libsvm"
+    p.write_text("1 3:1 2:1\n")
+    with pytest.raises(agd.NativeError, match="line 1: indices must be one-based and ascending"):
+        agd.MLUtils.loadLibSVMFile(ctx, str(p))
+
+
 @pytest.mark.gpu
 def test_load_libsvm_and_run(agd, ctx, oracle, tmp_path):
     rng = np.random.default_rng(0)
