@@ -41,7 +41,10 @@ enum { AGD_F64 = 0, AGD_F32 = 1, AGD_BF16 = 2 };
 /* agd_params.flags */
 enum {
   AGD_FLAG_MEMOIZE_FX = 1, /* reuse (f_x, g_x) of AGD.scala:269 for the history pass at :304 when x is
-                              unchanged (bit-identical result, 3 -> 2 passes per iteration) */
+                              unchanged (bit-identical result, 3 -> 2 passes per iteration).  Where the shard's kernel has a
+                              two-gradient form, applySmooth(x) then shares its sweep with applySmooth(y) of the NEXT
+                              iteration (y guessed from "accepted, no restart"; a wrong guess is discarded, a restart reuses
+                              (f_x, g_x) because then y = x): an accepted iteration reads X once. */
   AGD_FLAG_NO_FUSE = 2,    /* by default the history evaluation applySmooth(x) of AGD.scala:304 rides along with
                               applySmooth(y) of the NEXT iteration (AGD.scala:250) in one sweep over the shards: the same
                               evaluations and the same results bit for bit (dense shards), one read of X fewer per iteration.
@@ -182,6 +185,12 @@ int agd_smooth(agd_handle *h, int32_t gradient, const double *w, double *loss, d
  * (tcgen05 bf16 path, d below one 16-row tile); agd_run then simply does not fuse. */
 int agd_smooth_pair(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
                     int64_t *count, double *loss2);
+/* Two complete applySmooth evaluations (loss and gradient at w AND at w2) from ONE sweep over the shards -- what agd_run's
+ * memoised pass structure uses to evaluate applySmooth(x) of the backtracking test (AGD.scala:269) together with
+ * applySmooth(y) of the next iteration (:250).  Bit for bit what two agd_smooth calls return.  Dense fp32 / fp64 shards with
+ * at most 256 16-byte vectors per row (d <= 1024 fp32); fails elsewhere. */
+int agd_smooth_two(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
+                   int64_t *count, double *loss2, double *grad2);
 /* agd_prox = applyProjector (AGD.scala:214-222): Updater.compute(w, g, step, iter = 1, reg). */
 int agd_prox(agd_handle *h, int32_t updater, const double *w, const double *g, double step, double reg,
              int32_t d, double *w_out, double *reg_val);
@@ -208,7 +217,7 @@ int agd_gd_run_minibatch(agd_handle *h, int32_t gradient, int32_t updater, doubl
 /* Name of the gradient kernel the shard on local device `dev` dispatches to (for reports), "" when empty. */
 const char *agd_kernel_name(const agd_handle *h, int32_t dev);
 
-/* Options: "k1_variant" = auto|ring|generic|ws|tc, "collective" = auto|nccl|p2p, ring tuning knobs. */
+/* Options: "k1_variant" = auto|ring|generic|tc, "collective" = auto|nccl|p2p, ring tuning knobs. */
 int agd_set_option(agd_handle *h, const char *key, const char *value);
 
 #ifdef __cplusplus

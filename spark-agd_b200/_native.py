@@ -104,6 +104,8 @@ _SIGNATURES = {
                              C.POINTER(C.c_int64)]),
     "agd_smooth_pair": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "agd_smooth_two": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p,
+                                 C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_void_p]),
     "agd_prox": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
                            C.c_void_p, C.POINTER(C.c_double)]),
     "agd_run": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -83,7 +83,7 @@ struct Dev {
   Shard sh;
   // d-vectors of the driver loop (AGD.scala:224-230,241,249) + packed pass result
   double *x = nullptr, *z = nullptr, *x_old = nullptr, *z_old = nullptr, *y = nullptr, *g_y = nullptr,
-         *g_x = nullptr, *wtmp = nullptr, *acc = nullptr;
+         *g_x = nullptr, *wtmp = nullptr, *acc = nullptr, *y_spec = nullptr;
   int32_t vec_d = 0;
   double *slabs = nullptr;
   size_t slabs_doubles = 0;
@@ -120,10 +120,11 @@ struct agd_handle {
   bool comm_ready = false;
   bool comm_auto = false;   // the world is this process's own GPUs (agd_create): NCCL is only built if it is ever needed
   bool ipc_only = false;    // agd_comm_init_ipc: no NCCL at all, the host ships the CUDA IPC handles (agd_xchg_export/import)
-  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 3 warp-specialised, 4 tcgen05 (bf16)
+  int k1_variant = 0;  // 0 auto, 1 ring, 2 generic, 4 tcgen05 (bf16)
   int ring_stages = 0;
   int tune_rows = 0, tune_ctas = 0, tune_full = 0;
   int k1_diag = 0;
+  int tc_margins_f64 = 0;    // tcgen05 kernel: fp64-exact margins instead of the fp32 phase 1
   unsigned long long sample_seed = 0, sample_thresh = 0;  // mini-batch row mask of the current pass (0 = every row)
   int collective = 0;        // 0 = auto (peer memory if every pair of ranks can map each other, else NCCL), 1 = nccl, 2 = p2p
   int32_t x_d = 0;           // dimension the exchange buffers were built for (0 = not built)
@@ -195,7 +196,7 @@ int free_shard(agd_handle *h, Dev &D) {
 int ensure_vectors(agd_handle *h, Dev &D, int32_t d) {
   if (D.vec_d == d) return 0;
   CK(cudaSetDevice(D.ordinal));
-  double **v[] = {&D.x, &D.z, &D.x_old, &D.z_old, &D.y, &D.g_y, &D.g_x, &D.wtmp};
+  double **v[] = {&D.x, &D.z, &D.x_old, &D.z_old, &D.y, &D.g_y, &D.g_x, &D.wtmp, &D.y_spec};
   for (double **p : v) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -203,15 +204,16 @@ int ensure_vectors(agd_handle *h, Dev &D, int32_t d) {
     CK(cudaMemsetAsync(*p, 0, ((size_t)d + 4) * sizeof(double), D.st));
   }
   if (D.acc) cudaFree(D.acc);
-  CK(cudaMalloc(&D.acc, ((size_t)d + 4) * sizeof(double)));  // [grad(d) | loss | count | loss at w2 | count at w2]
+  // [grad(d) | loss | count | loss at w2 | count at w2], and after a two-gradient sweep a second block [grad at w2 | loss | count | 0 | 0]
+  CK(cudaMalloc(&D.acc, 2 * ((size_t)d + 4) * sizeof(double)));
   if (D.partials) cudaFree(D.partials);
   CK(cudaMalloc(&D.partials, (size_t)k3_blocks(d) * K3_NS * sizeof(double)));
   D.vec_d = d;
   return 0;
 }
 
-int ensure_slabs(agd_handle *h, Dev &D, int blocks, int32_t d) {
-  const size_t need = (size_t)blocks * ((size_t)d + 4);
+int ensure_slabs(agd_handle *h, Dev &D, int blocks, int32_t n) {
+  const size_t need = (size_t)blocks * (size_t)n;
   if (need <= D.slabs_doubles) return 0;
   CK(cudaSetDevice(D.ordinal));
   if (D.slabs) cudaFree(D.slabs);
@@ -346,7 +348,7 @@ int ensure_nccl(agd_handle *h) {
 // step 1 of the exchange setup: allocate this process's buffers for the current dimension and describe them
 int xchg_alloc(agd_handle *h, std::vector<XHandles> &mine) {
   const int W = h->world, nd = (int)h->devs.size();
-  const size_t n = (size_t)h->d + 4;
+  const size_t n = 2 * ((size_t)h->d + 4);   // room for a two-gradient sweep
   mine.assign((size_t)nd, XHandles());
   for (int i = 0; i < nd; ++i) {
     Dev &D = h->devs[i];
@@ -484,12 +486,11 @@ int ensure_xchg(agd_handle *h) {
 
 typedef const double *(*WSel)(Dev &);
 
-// which K1 kernel a dense shard of this handle runs on (0 generic, 1 ring, 2 warp-specialised, 3 tcgen05)
+// which K1 kernel a dense shard of this handle runs on (0 generic, 1 ring, 3 tcgen05)
 int dense_kernel_of(const agd_handle *h, int eb) {
   bool ring = k1_ring_supported(h->d, eb) != 0;
   if (h->k1_variant == 2) ring = false;
   if (k1_tc_supported(h->d, eb) && (h->k1_variant == 0 || h->k1_variant == 4)) return 3;
-  if (ring && h->k1_variant == 3) return 2;
   return ring ? 1 : 0;
 }
 
@@ -500,23 +501,36 @@ bool dual_supported(const agd_handle *h) {
     if (s.csr) continue;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     const int k = dense_kernel_of(h, eb);
-    if (k == 2 || k == 3) return false;
+    if (k == 3) return false;
     if (k == 1 && !k1_ring_dual_supported(h->d, eb)) return false;
+  }
+  return h->k1_diag == 0;
+}
+
+// ... and the gradient there too (the speculative sweep of the memoised pass structure)?
+bool dual_full_supported(const agd_handle *h) {
+  for (const Dev &D : h->devs) {
+    const Shard &s = D.sh;
+    if (s.csr) return false;
+    const int eb = s.elem_bytes ? s.elem_bytes : 4;
+    if (dense_kernel_of(h, eb) != 1 || !k1_ring_dual_full_supported(h->d, eb)) return false;
   }
   return h->k1_diag == 0;
 }
 
 // One applySmooth (AGD.scala:192-208) at the device-resident point `w_of(dev)`: K1 over every local
 // shard, slab reduction, one all-reduce of [grad | loss | count | loss2 | count2].  Result: Dev::acc on every device.
-// w2_of != nullptr: the same sweep also evaluates the loss (not the gradient) at `w2_of(dev)` -> acc[d+2], acc[d+3].
-int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = nullptr) {
+// w2_of != nullptr: the same sweep also evaluates the loss (not the gradient) at `w2_of(dev)` -> acc[d+2], acc[d+3];
+// with dual_full also the gradient there -> a second block acc[d+4 .. 2d+7] = [grad | loss | count | 0 | 0].
+int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = nullptr, bool dual_full = false) {
   const int32_t d = h->d;
+  const int32_t n = (dual_full ? 2 : 1) * (d + 4);   // doubles this sweep produces and exchanges
   const bool p2p = h->world > 1 && h->x_p2p;
   const unsigned long long epoch = p2p ? ++h->x_epoch : 0ull;
   auto make_pub = [&](Dev &D, size_t i) {
     XchgPub pub;
     pub.peers = D.xpeers; pub.world = h->world; pub.my_rank = h->first_rank + (int)i; pub.buf = (int)(epoch & 1ull);
-    pub.n = d + 4; pub.epoch = epoch; pub.ticket = D.xticket;
+    pub.n = n; pub.epoch = epoch; pub.ticket = D.xticket;
     return pub;
   };
   for (size_t i = 0; i < h->devs.size(); ++i) {
@@ -525,6 +539,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     const Shard &s = D.sh;
     const bool t0 = timed && i == 0;
     if (s.csr) {
+      if (dual_full) return fail(h, "internal: two-gradient sweep requested on a CSR shard");
       K1CsrArgs a;
       a.rowptr = s.rowptr; a.idx = s.idx; a.val = s.val; a.labels = s.labels; a.w = w_of(D);
       a.w2 = w2_of ? w2_of(D) : nullptr;
@@ -538,34 +553,36 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
       continue;
     }
     K1Args a;
-    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.w2 = w2_of ? w2_of(D) : nullptr; a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
-    a.stages = h->ring_stages; a.slab_stride = d + 4;
+    a.X = s.X; a.labels = s.labels; a.w = w_of(D); a.w2 = w2_of ? w2_of(D) : nullptr; a.dual_full = dual_full ? 1 : 0;
+    a.rows = s.rows; a.d = d; a.kind = h->k1_diag ? h->k1_diag : kind;
+    a.stages = h->ring_stages; a.slab_stride = n;
     a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune_rows = h->tune_rows; a.tune_ctas = h->tune_ctas; a.tune_full = h->tune_full;
+    a.tc_margins_f64 = h->tc_margins_f64;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     bool ring = k1_ring_supported(d, eb) != 0;
     if (h->k1_variant == 2) ring = false;
-    const bool ws = ring && h->k1_variant == 3;
     const bool tc = k1_tc_supported(d, eb) && (h->k1_variant == 0 || h->k1_variant == 4);
     if (h->k1_variant == 4 && !tc) return fail(h, "tcgen05 kernel needs bf16 storage with d %% 128 == 0 and d <= 4096 (d=%d)", d);
-    if ((h->k1_variant == 1 || h->k1_variant == 3) && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
-    if (a.w2 && (tc || ws || (ring && !k1_ring_dual_supported(d, eb))))
+    if (h->k1_variant == 1 && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
+    if (a.w2 && (tc || (ring && !k1_ring_dual_supported(d, eb))))
       return fail(h, "internal: two-point sweep requested on a kernel without one");
+    if (dual_full && (tc || !ring || !k1_ring_dual_full_supported(d, eb)))
+      return fail(h, "internal: two-gradient sweep requested on a kernel without one");
     int max_blocks = k1_max_blocks(D.sm_count);
     if (!ring) {  // generic: bound the slab memory for very wide rows
       const long long lim = (32LL << 20) / ((long long)d + 4);
       if (lim < max_blocks) max_blocks = lim < 1 ? 1 : (int)lim;
     }
-    if (ensure_slabs(h, D, max_blocks, d)) return 1;
+    if (ensure_slabs(h, D, max_blocks, n)) return 1;
     a.slabs = D.slabs;
     int blocks = 0;
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
     if (tc) CK(k1_tc_launch(a, D.sm_count, &blocks, D.st));
-    else if (ws) CK(k1_ws_launch(a, eb, D.sm_count, &blocks, D.st));
     else if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
     else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-    if (p2p) { const XchgPub pub = make_pub(D, i); CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, &pub, D.st)); }
-    else CK(k1_reduce_launch(D.slabs, blocks, d, s.rows, D.acc, nullptr, D.st));
+    if (p2p) { const XchgPub pub = make_pub(D, i); CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, &pub, D.st)); }
+    else CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, nullptr, D.st));
     if (i == 0) h->launches += (s.rows > 0 ? 2 : 1);
   }
   if (p2p) {  // K2': every rank already holds every rank's partial sums; add them in rank order
@@ -573,7 +590,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     for (Dev &D : h->devs) {
       CK(cudaSetDevice(D.ordinal));
-      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), d + 4, epoch, D.acc, D.st));
+      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, epoch, D.acc, D.st));
     }
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     h->launches += 1;
@@ -584,7 +601,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     Dev &D0 = h->devs[0];
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     CKN(N.GroupStart());
-    for (Dev &D : h->devs) CKN(N.AllReduce(D.acc, D.acc, (size_t)d + 4, ncclDouble, ncclSum, D.comm, D.st));
+    for (Dev &D : h->devs) CKN(N.AllReduce(D.acc, D.acc, (size_t)n, ncclDouble, ncclSum, D.comm, D.st));
     CKN(N.GroupEnd());
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     h->collectives += 1;
@@ -747,7 +764,7 @@ int agd_destroy(agd_handle *h) {
     if (D.comm && nccl_api().ok) nccl_api().CommDestroy(D.comm);
     D.comm = nullptr;
     free_shard(h, D);
-    double *v[] = {D.x, D.z, D.x_old, D.z_old, D.y, D.g_y, D.g_x, D.wtmp, D.acc, D.slabs, D.partials};
+    double *v[] = {D.x, D.z, D.x_old, D.z_old, D.y, D.g_y, D.g_x, D.wtmp, D.y_spec, D.acc, D.slabs, D.partials};
     for (double *p : v)
       if (p) cudaFree(p);
     if (D.ticket) cudaFree(D.ticket);
@@ -1145,7 +1162,6 @@ const char *agd_kernel_name(const agd_handle *h, int32_t dev) {
   static thread_local char buf[96];
   switch (dense_kernel_of(h, eb)) {
     case 3: return "k1_tc_kernel (tcgen05, bf16 storage)";
-    case 2: snprintf(buf, sizeof buf, "k1_ws_kernel<%s,...>", t); return buf;
     case 1: snprintf(buf, sizeof buf, "k1_ring_kernel<%s,...>", t); return buf;
     default: snprintf(buf, sizeof buf, "k1_generic_kernel<%s>", t); return buf;
   }
@@ -1157,9 +1173,8 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
     if (!strcmp(value, "auto")) h->k1_variant = 0;
     else if (!strcmp(value, "ring")) h->k1_variant = 1;
     else if (!strcmp(value, "generic")) h->k1_variant = 2;
-    else if (!strcmp(value, "ws")) h->k1_variant = 3;
     else if (!strcmp(value, "tc")) h->k1_variant = 4;
-    else return fail(h, "k1_variant must be auto|ring|generic|ws|tc");
+    else return fail(h, "k1_variant must be auto|ring|generic|tc");
     return 0;
   }
   if (!strcmp(key, "ring_stages")) { h->ring_stages = atoi(value); return 0; }
@@ -1172,6 +1187,12 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
     return 0;
   }
   if (!strcmp(key, "k1_diag")) { h->k1_diag = atoi(value); return 0; }
+  if (!strcmp(key, "tc_margins")) {
+    if (!strcmp(value, "f32")) h->tc_margins_f64 = 0;
+    else if (!strcmp(value, "f64")) h->tc_margins_f64 = 1;
+    else return fail(h, "tc_margins must be f32|f64");
+    return 0;
+  }
   if (!strcmp(key, "ring_rows")) { h->tune_rows = atoi(value); return 0; }
   if (!strcmp(key, "ring_ctas")) { h->tune_ctas = atoi(value); return 0; }
   if (!strcmp(key, "ring_predicated")) { h->tune_full = atoi(value); return 0; }
@@ -1180,11 +1201,12 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
 
 // ---------------------------------------------------------------- applySmooth with host buffers
 static int smooth_host(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
-                       int64_t *count, double *loss2) {
+                       int64_t *count, double *loss2, double *grad2 = nullptr) {
   if (check_ready(h)) return 1;
   if (gradient < 0 || gradient > AGD_GRAD_LEAST_SQUARES_HALF) return fail(h, "unknown gradient %d", gradient);
   if (!w || !loss || !grad) return fail(h, "NULL argument");
   if (w2 && !dual_supported(h)) return fail(h, "this shard's gradient kernel has no two-point form (use two agd_smooth calls)");
+  if (grad2 && !dual_full_supported(h)) return fail(h, "this shard's gradient kernel has no two-gradient form (use two agd_smooth calls)");
   const int32_t d = h->d;
   for (Dev &D : h->devs) {
     CK(cudaSetDevice(D.ordinal));
@@ -1198,18 +1220,22 @@ static int smooth_host(agd_handle *h, int32_t gradient, const double *w, const d
   h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
   h->launches = h->collectives = 0;
   if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.wtmp; }, false,
-                    w2 ? (WSel)[](Dev &D) { return (const double *)D.g_x; } : (WSel) nullptr))
+                    w2 ? (WSel)[](Dev &D) { return (const double *)D.g_x; } : (WSel) nullptr, grad2 != nullptr))
     return 1;
   Dev &D0 = h->devs[0];
   CK(cudaSetDevice(D0.ordinal));
-  std::vector<double> host((size_t)d + 4);
-  CK(cudaMemcpyAsync(host.data(), D0.acc, ((size_t)d + 4) * sizeof(double), cudaMemcpyDeviceToHost, D0.st));
+  std::vector<double> host(2 * ((size_t)d + 4));
+  CK(cudaMemcpyAsync(host.data(), D0.acc, (grad2 ? 2 : 1) * ((size_t)d + 4) * sizeof(double), cudaMemcpyDeviceToHost, D0.st));
   for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
   const double cnt = host[(size_t)d + 1];
   *loss = host[d] / cnt;                                    // AGD.scala:207
   for (int32_t j = 0; j < h->d_user; ++j) grad[j] = host[j] / cnt;
   if (count) *count = (int64_t)cnt;
   if (w2 && loss2) *loss2 = host[(size_t)d + 2] / host[(size_t)d + 3];
+  if (grad2) {  // second block: [grad at w2 | loss | count | 0 | 0]
+    const double *b2 = host.data() + (size_t)d + 4;
+    for (int32_t j = 0; j < h->d_user; ++j) grad2[j] = b2[j] / b2[(size_t)d + 1];
+  }
   return 0;
 }
 
@@ -1221,6 +1247,12 @@ int agd_smooth_pair(agd_handle *h, int32_t gradient, const double *w, const doub
                     int64_t *count, double *loss2) {
   if (h && (!w2 || !loss2)) return fail(h, "NULL argument");
   return smooth_host(h, gradient, w, w2, loss, grad, count, loss2);
+}
+
+int agd_smooth_two(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
+                   int64_t *count, double *loss2, double *grad2) {
+  if (h && (!w2 || !loss2 || !grad2)) return fail(h, "NULL argument");
+  return smooth_host(h, gradient, w, w2, loss, grad, count, loss2, grad2);
 }
 
 // ---------------------------------------------------------------- applyProjector with host buffers
@@ -1268,6 +1300,14 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   // (first backtracking round) do not depend on each other, so ONE sweep over X evaluates both.
   const bool fuse = (p->flags & AGD_FLAG_NO_FUSE) == 0 && dual_supported(h);
   bool y_ready = false;   // acc already holds applySmooth(y) for the first round of the coming iteration
+  // Speculative sweep of the memoised pass structure: applySmooth(x) of the backtracking test (:269) and applySmooth(y) of the
+  // NEXT iteration (:250) -- y_{k+1} = x_k (1 - theta') + z_k theta' with theta' from L alpha, i.e. assuming the test accepts and
+  // the gradient test does not restart -- are evaluated by ONE two-gradient sweep over X.  An accepted iteration then reads X
+  // once.  Every evaluation is the arithmetic a sweep of its own would do (same kernel code path), so weights and history
+  // stay bit-identical; a rejected guess only wastes the extra FMAs.  On a restart y_{k+1} = x_k exactly, and the memoised
+  // (f_x, g_x) are reused without any evaluation at all.
+  const bool speculate_y = memoize && (p->flags & AGD_FLAG_NO_FUSE) == 0 && p->beta < 1.0 && dual_full_supported(h);
+  size_t acc_off = 0;     // where applySmooth(y) of the current round lives inside Dev::acc (0, or d + 4 after a good guess)
 
   for (Dev &D : h->devs) {                                                 // :224-225  x = w0 ; z = x
     CK(cudaSetDevice(D.ordinal));
@@ -1312,6 +1352,8 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     L = L * p->alpha;                                                      // :243
     const double theta_old = theta;                                        // :244
     bool nonterminating = false, have_fx = false, first_round = true;
+    bool guess_live = false;     // acc[d+4 ..] holds applySmooth at y_spec, sharing its sweep with this round's applySmooth(x)
+    double guess_theta = 0.0;
     double f_x = 0.0;
     for (;;) {                                                             // :246
       theta = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L / L_old) / (theta_old * theta_old)));  // :248
@@ -1320,20 +1362,35 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
         if (!y_ready && launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt, theta, d, D.st); })) return 1;
         first_round = false;
       } else if (launch_all([&](Dev &D) { return k3_combine_launch(D.y, D.x_old, omt, D.z_old, theta, d, D.st); })) return 1;  // :249
-      if (!y_ready && smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
+      if (!y_ready) {
+        if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
+        acc_off = 0;
+      }
       y_ready = false;
       s.passes++;
       const double step = 1.0 / (theta * L);                               // :253
+      const bool speculate = beta < 1.0;                                   // :257 is known up front
+      // this round's applySmooth(x) sweep also carries a guess of y_{k+1} (formed inside k3_step from the new x and z)
+      const bool guessed = speculate && speculate_y && nIter < p->num_iterations;
+      double theta_guess = 0.0;
+      if (guessed) {
+        const double L_n = L * p->alpha;                                   // :243-248 of iteration nIter + 1 if this round accepts
+        theta_guess = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L_n / L) / (theta * theta)));
+      }
       if (launch_all([&](Dev &D) {                                         // :254-255,263-264 fused
             K3StepArgs a;
-            a.acc = D.acc; a.x_old = D.x_old; a.z_old = D.z_old; a.y = D.y; a.g_y = D.g_y; a.z = D.z; a.x = D.x;
+            a.y_spec = guessed ? D.y_spec : nullptr; a.spec_ca = 1.0 - theta_guess; a.spec_cb = theta_guess;
+            a.acc = D.acc + acc_off; a.x_old = D.x_old; a.z_old = D.z_old; a.y = D.y; a.g_y = D.g_y; a.z = D.z; a.x = D.x;
             a.partials = D.partials; a.ticket = D.ticket; a.scalars = D.scalars_dev;
             a.theta = theta; a.one_minus_theta = omt; a.step = step; a.reg = p->reg_param; a.d = d; a.updater = p->updater;
             return k3_step_launch(a, D.st);
           })) return 1;
-      const bool speculate = beta < 1.0;                                   // :257 is known up front
       if (speculate) {                                                     // :269, enqueued before :265 is known
-        if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
+        if (guessed) {
+          if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true,
+                            [](Dev &D) { return (const double *)D.y_spec; }, true))
+            return 1;
+        } else if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
         if (launch_all([&](Dev &D) {
               K3GxArgs a;
               a.acc = D.acc; a.x = D.x; a.y = D.y; a.g_y = D.g_y; a.g_x = D.g_x; a.partials = D.partials;
@@ -1348,10 +1405,12 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       if (beta >= 1.0) break;                                              // :257
       const double nxy = std::sqrt(sc[0]);
       const double xy_sq = nxy * nxy;                                      // :264  math.pow(norm(xy), 2)
-      if (xy_sq == 0) { s.wasted_passes++; break; }                        // :265  (the speculative pass is discarded)
+      if (xy_sq == 0) { s.wasted_passes++; guess_live = false; break; }    // :265  (the speculative pass is discarded)
       s.passes++;
       f_x = sg[6] / sg[7];
       have_fx = true;
+      guess_live = guessed;                                                // valid only if this round is the accepted one
+      guess_theta = theta_guess;
       double localL;
       if (backtrack_simple) {                                              // :272
         const double q_x = f_y + sc[1] + 0.5 * L * xy_sq;                  // :273
@@ -1365,6 +1424,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       else localL = L;                                                     // :288-290
       L = jmin(Lexact, jmax(localL, L / beta));                            // :292
       s.backtracks++;
+      if (guess_live) { s.wasted_passes++; guess_live = false; }   // rejected: y_{k+1} was guessed from an L that did not survive
       if (L != L) { nonterminating = true; break; }  // the reference never leaves :246-293 once L is NaN
     }
     const double c_x = reg_value(p->updater, p->reg_param, sc[2], sc[5]);  // :305  applyProjector(x, g_x, 0.0)._1
@@ -1401,6 +1461,22 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       backtrack_simple = true;                                             // :330
       s.restarts++;
     }
+    if (speculate_y && have_fx && !stop && nIter < p->num_iterations && (guess_live || restart)) {
+      // The coming iteration's first round is already evaluated.  (x_old, z_old) = (x, z) and y (:241,:249) are formed as the
+      // loop head would form them -- the same kernel, the same doubles -- and pass 1 is skipped (y_ready):
+      //   * no restart: y_{k+1} is the guess; its sums are the second block of acc;
+      //   * restart: theta' = 1, so y_{k+1} = x_k * 0 + z * 1 with z = x_k (:328) = x_k exactly; applySmooth(x_k) is the first block.
+      const double L_n = L * p->alpha;
+      const double theta_n = 2.0 / (1.0 + std::sqrt(1.0 + 4.0 * (L_n / L) / (theta * theta)));
+      if (restart || theta_n == guess_theta) {
+        const double omt_n = 1.0 - theta_n;
+        if (launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt_n, theta_n, d, D.st); })) return 1;
+        acc_off = restart ? 0 : (size_t)d + 4;
+        if (restart && guess_live) s.wasted_passes++;
+        if (!restart) s.fused_passes++;      // pass 1 of iteration nIter + 1 shared its sweep with pass 2 of this one
+        y_ready = true;
+      } else if (guess_live) s.wasted_passes++;
+    } else if (guess_live) s.wasted_passes++;
     if (fuse_now) {
       // :243-249 of iteration nIter + 1, first round (the loop head recomputes the same doubles), then one sweep:
       // acc[0..d+1] = applySmooth(y) sums, acc[d+2..d+3] = loss sum / count at x

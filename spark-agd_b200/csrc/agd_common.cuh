@@ -13,7 +13,8 @@ struct K1Args {
   const void *X;          // shard, row-major, ld == d, element type float or double
   const double *labels;   // rows (+ padding)
   const double *w;        // d doubles (device)
-  const double *w2;       // optional second point of a fused sweep (AGD.scala:304 riding along with :250): loss only
+  const double *w2;       // optional second point of a fused sweep (AGD.scala:304 riding along with :250): loss only ...
+  int32_t dual_full;      // ... unless dual_full: loss AND gradient at w2 (second slab block of d + 4 doubles; ring kernel, fp32/fp64)
   double *slabs;          // [grid][d + 4]: per-block column sums of loss' * x, the loss sum, the row count at w; loss sum, count at w2
   int64_t rows;           // rows in the shard
   int32_t d;
@@ -25,13 +26,14 @@ struct K1Args {
   int32_t tune_rows;      // 0 = default; rows per tile of the headline ring shape (4|8)
   int32_t tune_ctas;      // 0 = default; resident CTAs per SM (1|2|3)
   int32_t tune_full;      // 0 = default; 1 = keep the column predicates even when every thread owns whole vectors
+  int32_t tc_margins_f64; // tcgen05 kernel: 1 = fp64-exact margins on the CUDA cores (option tc_margins=f64), 0 = fp32 (default)
 };
 
 // launch helpers (k1_dense.cu); return the number of blocks that wrote a slab
 int k1_ring_supported(int32_t d, int elem_bytes);
 int k1_ring_dual_supported(int32_t d, int elem_bytes);
 cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
-cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st);
+int k1_ring_dual_full_supported(int32_t d, int elem_bytes);
 cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
                               cudaStream_t st);
 int k1_max_blocks(int sm_count);
@@ -59,11 +61,10 @@ cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStrea
 cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
                                unsigned long long epoch, double *acc_out, cudaStream_t st);
 
-// out[c] = sum_b slabs[b][c] for c <= d + 3 (gradient sums, loss sum, row count, loss sum and count at w2; fixed order =>
+// out[c] = sum_b slabs[b][c] for c < n, n = d + 4 or 2 (d + 4) (gradient sums, loss sum, row count, loss sum and count at w2; fixed order =>
 // deterministic);
 // with pub != nullptr the sums are also stored into every peer's exchange slot and the epoch flag is raised
-cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, const XchgPub *pub,
-                             cudaStream_t st);
+cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t n, double *out, const XchgPub *pub, cudaStream_t st);
 
 // CSR variant (k1_csr.cu)
 struct K1CsrArgs {
@@ -96,6 +97,8 @@ struct K3StepArgs {
   double *scalars;        // [K3_NS]: S(x-y)^2, (x-y).g_y, S x^2, S (x-x_old)^2, g_y.(x-x_old), S|x|, loss_sum, count
   double theta, one_minus_theta, step, reg;
   int32_t d, updater;
+  double *y_spec;         // optional: y_spec = x * spec_ca + z * spec_cb, the guessed y of the next iteration (speculative sweep)
+  double spec_ca, spec_cb;
 };
 cudaError_t k3_step_launch(const K3StepArgs &a, cudaStream_t st);
 struct K3GxArgs {

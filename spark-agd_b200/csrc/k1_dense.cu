@@ -100,27 +100,54 @@ __host__ __device__ inline uint32_t round_up_u32(uint32_t v, uint32_t a) { retur
 
 // shared-memory carve-up (identical on host and device)
 struct RingLayout {
-  uint32_t stage_stride, aux_off, aux2_off, partial_off, partial2_off, mult_off, red_off, cnt_off, bars_off, total;
+  uint32_t stage_stride, aux_off, partial_off, partial2_off, mult_off, mult2_off, red_off, cnt_off, bars_off, total;
 };
-// dual = the launch also evaluates the loss at a second point w2 (pass fusion): a second w staging area and a second
-// set of per-warp partial dots
-__host__ __device__ inline RingLayout ring_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages, bool dual) {
+// mode: 0 = one point; 1 = the launch also evaluates the LOSS at a second point w2 (pass fusion of the history evaluation);
+// 2 = loss AND gradient at w2 (the speculative sweep of the memoised pass structure).  aux holds w (and w2) in the
+// conflict-free plane layout described at the kernel.
+__host__ __device__ inline RingLayout ring_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages, int mode) {
   RingLayout L;
   L.stage_stride = round_up_u32(tile_bytes, 128);
   L.aux_off = L.stage_stride * stages;
-  L.aux2_off = L.aux_off + round_up_u32(aux_bytes, 128);
-  L.partial_off = L.aux2_off + (dual ? round_up_u32(aux_bytes, 128) : 0u);
+  L.partial_off = L.aux_off + round_up_u32(aux_bytes, 128);
   L.partial2_off = L.partial_off + kMaxTileRows * 8 * 8;
-  L.mult_off = L.partial2_off + (dual ? kMaxTileRows * 8 * 8 : 0);
-  L.red_off = L.mult_off + kMaxTileRows * 8;
+  L.mult_off = L.partial2_off + (mode ? kMaxTileRows * 8 * 8 : 0);
+  L.mult2_off = L.mult_off + kMaxTileRows * 8;
+  L.red_off = L.mult2_off + (mode == 2 ? kMaxTileRows * 8 : 0);
   L.cnt_off = L.red_off + 32 * 8;
   L.bars_off = L.cnt_off + round_up_u32(stages * 4, 8);
   L.total = L.bars_off + (stages + 1) * 8;
   return L;
 }
 
+// Row permutation that makes the warp transpose-reduce select-free: register r of a lane holds tile row r ^ row_perm<R>(lane).
+// Level (bit, width) of warp_rows_reduce_perm pairs lane L with L ^ bit and folds registers i and i + width; because the
+// partner's permutation differs exactly in `width`, its register i + width holds the SAME row as this lane's register i,
+// so every level is "p[i] += shfl_xor(p[i + width])" with no lane-dependent selects (4 FSEL per pair before).
+template <int R>
+__device__ __forceinline__ int row_perm(int lane) {
+  int m = 0, bit = 16;
+#pragma unroll
+  for (int width = R / 2; width >= 1; width >>= 1, bit >>= 1) m |= (lane & bit) ? width : 0;
+  return m;
+}
+// afterwards every lane holds the warp total of row row_perm<R>(lane); the pairings -- and therefore the bits -- are those of
+// warp_rows_reduce (k1_device.cuh)
+template <int R>
+__device__ __forceinline__ double warp_rows_reduce_perm(double (&p)[R]) {
+  int bit = 16;
+#pragma unroll
+  for (int width = R / 2; width >= 1; width >>= 1, bit >>= 1) {
+#pragma unroll
+    for (int i = 0; i < width; ++i) p[i] = p[i] + __shfl_xor_sync(0xffffffffu, p[i + width], bit);
+  }
+  double tot = p[0];
+  for (; bit >= 1; bit >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, bit);
+  return tot;
+}
+
 // ---------------------------------------------------------------- the hot kernel
-template <typename T, int NT, int TPR, int V, int R, int MINB, bool DUAL>
+template <typename T, int NT, int TPR, int V, int R, int MINB, int MODE>
 __global__ void __launch_bounds__(NT, MINB)
 k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uint32_t aux_bytes) {
   constexpr int EPV = Elem<T>::EPV;
@@ -128,24 +155,28 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
   constexpr int WPG = TPR / 32;         // warps per row group
   constexpr int TR = NG * R;            // rows per tile
   constexpr int NW = NT / 32;
+  constexpr bool DUAL = MODE != 0;      // a second point rides along (its loss; with MODE == 2 its gradient too)
+  constexpr int NP = DUAL ? 2 : 1;      // points per sweep
+  constexpr int NCH = EPV / 2;          // 16-byte chunks per fp64-widened vector
   static_assert(TR <= kMaxTileRows && TR % 2 == 0 && (NW & (NW - 1)) == 0, "tile rows / warps");
   // DUAL: lanes 0-15 of the scalar warp evaluate the rows at w, lanes 16-31 the same rows at w2
   static_assert(!DUAL || TR <= 16, "pass fusion needs the tile's rows twice in one warp");
-  // two accumulator sets (even / odd rows) halve the DFMA dependency chains; with V * EPV > 4 columns per thread there are
-  // enough independent chains already
-  constexpr bool kSplitAcc = R > 1 && V * EPV <= 4;
+  // One accumulator set per point in every mode, so a point's sums do not depend on which sweep form evaluated it (the
+  // fused / memoised / plain pass structures agree bit for bit).  Round 1 kept two sets (even / odd rows) for narrow threads;
+  // measured on the headline shard (tools/k1_modes.py, same box): one-point 7.11 -> 7.27 ms without them, two-point equal,
+  // and the two-gradient sweep 10.05 -> 9.15 ms because its four sets spilled.
   extern __shared__ __align__(128) unsigned char smem[];
 
   const int S = a.stages;
   const uint32_t row_bytes = (uint32_t)a.d * (uint32_t)sizeof(T);
-  const RingLayout L = ring_layout(TR * row_bytes + kMaxTileRows * 8, aux_bytes, S, DUAL);  // rows, then their labels
-  double *aux = reinterpret_cast<double *>(smem + L.aux_off);
-  double *aux2 = reinterpret_cast<double *>(smem + L.aux2_off);        // w2 (DUAL)
+  const RingLayout L = ring_layout(TR * row_bytes + kMaxTileRows * 8, aux_bytes, S, MODE);  // rows, then their labels
+  unsigned char *aux = smem + L.aux_off;                               // w [and w2] planes; reused for the row-group reduce
   double *partial = reinterpret_cast<double *>(smem + L.partial_off);  // [TR][8]
   double *partial2 = reinterpret_cast<double *>(smem + L.partial2_off);  // [TR][8] at w2 (DUAL)
   double *mult_s = reinterpret_cast<double *>(smem + L.mult_off);      // [TR]
+  double *mult2_s = reinterpret_cast<double *>(smem + L.mult2_off);    // [TR] at w2 (MODE 2)
   double *red = reinterpret_cast<double *>(smem + L.red_off);
-  unsigned int *cnt = reinterpret_cast<unsigned int *>(smem + L.cnt_off);  // [S] warps done with the stage
+  unsigned int *cnt = reinterpret_cast<unsigned int *>(smem + L.cnt_off);  // [S] warps done with the stage (diagnostic modes)
   const uint32_t bars = smem_u32(smem + L.bars_off);                   // full[s] = bars + 8*s ; wbar = bars + 8*S
   const uint32_t wbar = bars + 8u * S;
   const unsigned char *Xb = reinterpret_cast<const unsigned char *>(a.X);
@@ -164,6 +195,8 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride), Xb + (size_t)row0 * row_bytes, rv * row_bytes, full);
     tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride + TR * row_bytes), a.labels + row0, lbytes, full);
   };
+  // one point's share of the w staging area: TPR * V vectors of EPV doubles (>= d doubles: columns past d are zero weights)
+  constexpr uint32_t kPointBytes = (uint32_t)TPR * V * EPV * 8u;
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bars + 8u * s, 1);
@@ -171,23 +204,54 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     }
     mbar_init(wbar, 1);
     mbar_fence_init();
-    mbar_expect_tx(wbar, (uint32_t)a.d * 8u * (DUAL ? 2u : 1u));
+    mbar_expect_tx(wbar, (uint32_t)a.d * 8u * NP);
     tma_bulk_g2s(smem_u32(aux), a.w, (uint32_t)a.d * 8u, wbar);  // w: TMA-staged once per CTA
-    if (DUAL) tma_bulk_g2s(smem_u32(aux2), a.w2, (uint32_t)a.d * 8u, wbar);
+    if (DUAL) tma_bulk_g2s(smem_u32(aux + kPointBytes), a.w2, (uint32_t)a.d * 8u, wbar);
     for (int s = 0; s < S; ++s) fill(s, s);
   }
   __syncthreads();
 
   const int g = tid / TPR, t = tid % TPR, wig = t >> 5;
   const bool full_row = nvec == V * TPR && a.tune_full == 0;
-  double acc[V][EPV], acc2[V][EPV];
-  mbar_wait(wbar, 0);  // w is in shared memory; it is re-read per tile so that it is not live across phase 2
+  const int rperm = row_perm<R>(lane);   // register r of this lane holds tile row g * R + (r ^ rperm)
+  mbar_wait(wbar, 0);
+  // Re-lay w (and w2) out once per CTA, in place through registers, from the linear order TMA delivered into PLANES: chunk c
+  // (16 bytes = 2 doubles) of vector v of point q for thread t sits at ((v * NCH + c) * NP + q) * TPR + t.  The per-tile
+  // re-read (w is not kept live across phase 2) is then one conflict-free LDS.128 per chunk -- in the linear order a thread's
+  // 32-byte stride made every such read a 2-way bank conflict -- and columns past d read as exact zeros without predicates.
+  {
+    double wtmp[NP][V][EPV];
+    if (tid < TPR) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const int vec = v * TPR + t;
+#pragma unroll
+          for (int e = 0; e < EPV; ++e)
+            wtmp[q][v][e] = vec < nvec ? reinterpret_cast<const double *>(aux + q * kPointBytes)[vec * EPV + e] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid < TPR) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            *reinterpret_cast<double2 *>(aux + ((size_t)((v * NCH + c) * NP + q) * TPR + t) * 16) =
+                make_double2(wtmp[q][v][2 * c], wtmp[q][v][2 * c + 1]);
+    }
+    __syncthreads();
+  }
+  double acc[V][EPV], accB[MODE == 2 ? V : 1][MODE == 2 ? EPV : 1];   // gradient at w; at w2 (MODE 2)
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int e = 0; e < EPV; ++e) {
       acc[v][e] = 0.0;
-      acc2[v][e] = 0.0;
+      if (MODE == 2) accB[MODE == 2 ? v : 0][MODE == 2 ? e : 0] = 0.0;
     }
   double lossacc = 0.0, cntacc = 0.0;
   const int rv_last = (int)(a.rows - (ntiles - 1) * TR);
@@ -210,36 +274,25 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     if (sactive)
       ylab = *reinterpret_cast<const double *>(smem + (size_t)s * L.stage_stride + TR * row_bytes + srow * 8);
 
-    double wreg[V][EPV];
     // pull this thread's R x V vectors out of the stage and widen them to fp64 once
     double xd[R][V][EPV];
     const unsigned char *stage = smem + (size_t)s * L.stage_stride;
     if (full_row) {  // every thread owns V whole vectors of the row (d = 1024 fp32 ...): no predicates, no zero fill
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) wreg[v][e] = aux[(v * TPR + t) * EPV + e];
-#pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          const uint4 raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)(v * TPR + t) * 16);
+          const uint4 raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + (r ^ rperm)) * row_bytes + (size_t)(v * TPR + t) * 16);
           cvt_vec<T, EPV>(raw, xd[r][v]);
         }
     } else {
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int vec = v * TPR + t;
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
-      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const int vec = v * TPR + t;
           uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-          if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)vec * 16);
+          if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + (r ^ rperm)) * row_bytes + (size_t)vec * 16);
           cvt_vec<T, EPV>(raw, xd[r][v]);
         }
       }
@@ -247,12 +300,31 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     if (rv < TR) {  // ragged last tile: rows past the shard hold stale bytes
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (g * R + r >= rv) {
+        if (g * R + (r ^ rperm) >= rv) {
 #pragma unroll
           for (int v = 0; v < V; ++v)
 #pragma unroll
             for (int e = 0; e < EPV; ++e) xd[r][v][e] = 0.0;
         }
+    }
+    // this tile's weights out of the planes (conflict-free LDS.128).  Threads that own few columns (V * EPV <= 4) fetch them
+    // up front; wide threads fetch each 16-byte chunk right where phase 1 consumes it (kJit), which keeps them spill-free.
+    auto wplane = [&](int q, int v, int c) {
+      return *reinterpret_cast<const double2 *>(aux + ((size_t)((v * NCH + c) * NP + q) * TPR + t) * 16);
+    };
+    constexpr bool kJit = V * EPV > 4;
+    double wreg[NP][kJit ? 1 : V][kJit ? 1 : EPV];
+    if (!kJit) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            const double2 wv = wplane(q, v, c);
+            wreg[q][kJit ? 0 : v][kJit ? 0 : 2 * c] = wv.x;
+            wreg[q][kJit ? 0 : v][kJit ? 0 : 2 * c + 1] = wv.y;
+          }
     }
     if (a.kind == 100 || a.kind == 101) {  // diagnostics (option k1_diag): 100 = stream + widen only, 101 = + phase 1, no barriers
       __syncwarp();
@@ -269,42 +341,55 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
 #pragma unroll
         for (int v = 0; v < V; ++v)
 #pragma unroll
-          for (int e = 0; e < EPV; ++e) sacc = (a.kind == 100) ? sacc + xd[r][v][e] : fma(xd[r][v][e], wreg[v][e], sacc);
+          for (int e = 0; e < EPV; ++e) {
+            const double we = kJit ? (e & 1 ? wplane(0, v, e / 2).y : wplane(0, v, e / 2).x) : wreg[0][kJit ? 0 : v][kJit ? 0 : e];
+            sacc = (a.kind == 100) ? sacc + xd[r][v][e] : fma(xd[r][v][e], we, sacc);
+          }
       acc[0][0] += sacc;
       continue;
     }
 
-    // phase 1: R partial dots over this thread's columns
-    double p[R];
+    // phase 1: R partial dots over this thread's columns (against w, and against w2 on the same retained tile).  Either way
+    // every p[r] is the same (v, e)-ascending FMA chain, so the two forms (and the one- and two-point kernels) agree bit for bit.
+    if (kJit) {
+      double p[R], p2[DUAL ? R : 1];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      double sacc = 0.0;
+      for (int r = 0; r < R; ++r) { p[r] = 0.0; if (DUAL) p2[DUAL ? r : 0] = 0.0; }
 #pragma unroll
       for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) sacc = fma(xd[r][v][e], wreg[v][e], sacc);
-      p[r] = sacc;
-    }
-    const double tot = warp_rows_reduce<R>(p, lane);
-    if ((lane % (32 / R)) == 0) partial[(g * R + lane / (32 / R)) * 8 + wig] = tot;
-    if (DUAL) {  // the same retained tile against w2 (only the loss at w2 is wanted: no phase 2 for it)
+        for (int c = 0; c < NCH; ++c) {
+          const double2 wa = wplane(0, v, c);
+          const double2 wb = DUAL ? wplane(NP - 1, v, c) : wa;
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int vec = v * TPR + t;
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) wreg[v][e] = (full_row || vec < nvec) ? aux2[vec * EPV + e] : 0.0;
+          for (int r = 0; r < R; ++r) {
+            p[r] = fma(xd[r][v][2 * c + 1], wa.y, fma(xd[r][v][2 * c], wa.x, p[r]));
+            if (DUAL) p2[DUAL ? r : 0] = fma(xd[r][v][2 * c + 1], wb.y, fma(xd[r][v][2 * c], wb.x, p2[DUAL ? r : 0]));
+          }
+        }
+      const double tot = warp_rows_reduce_perm<R>(p);
+      if ((lane % (32 / R)) == 0) partial[(g * R + rperm) * 8 + wig] = tot;
+      if (DUAL) {
+        double (&pr)[R] = reinterpret_cast<double (&)[R]>(p2);
+        const double tot2 = warp_rows_reduce_perm<R>(pr);
+        if ((lane % (32 / R)) == 0) partial2[(g * R + rperm) * 8 + wig] = tot2;
       }
+    } else {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        double sacc = 0.0;
+      for (int q = 0; q < NP; ++q) {
+        double p[R];
 #pragma unroll
-        for (int v = 0; v < V; ++v)
+        for (int r = 0; r < R; ++r) {
+          double sacc = 0.0;
 #pragma unroll
-          for (int e = 0; e < EPV; ++e) sacc = fma(xd[r][v][e], wreg[v][e], sacc);
-        p[r] = sacc;
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) sacc = fma(xd[r][v][e], wreg[q][kJit ? 0 : v][kJit ? 0 : e], sacc);
+          p[r] = sacc;
+        }
+        const double tot = warp_rows_reduce_perm<R>(p);
+        if ((lane % (32 / R)) == 0) (q ? partial2 : partial)[(g * R + rperm) * 8 + wig] = tot;
       }
-      const double tot2 = warp_rows_reduce<R>(p, lane);
-      if ((lane % (32 / R)) == 0) partial2[(g * R + lane / (32 / R)) * 8 + wig] = tot2;
     }
     __syncthreads();
     // every warp holds its part of the tile in registers: the stage is free.  One lane of a warp that is not this tile's
@@ -327,25 +412,36 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       if (a.kind == AGD_GRAD_LOGISTIC) mult = logistic_head(m, ylab, mid);
       else loss_eval(a.kind, m, ylab, mult, loss);
       if (DUAL ? lane < 16 : srow < TR) mult_s[srow] = row_ok ? mult : 0.0;
+      if (MODE == 2 && lane >= 16) mult2_s[srow] = row_ok ? mult : 0.0;
       if (a.kind != AGD_GRAD_LOGISTIC) lossacc += row_ok ? loss : 0.0;
       cntacc += row_ok ? 1.0 : 0.0;
     }
     __syncthreads();
 
-    // phase 2: g += mult_i * x_i on the retained fp64 tile (two accumulator sets: dependency chains of R/2)
+    // phase 2: g += mult_i * x_i on the retained fp64 tile
     auto phase2 = [&]() {
       double mu[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) mu[r] = mult_s[g * R + r];
+      for (int r = 0; r < R; ++r) mu[r] = mult_s[g * R + (r ^ rperm)];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
 #pragma unroll
-          for (int e = 0; e < EPV; ++e) {
-            if (kSplitAcc && (r & 1)) acc2[v][e] = fma(mu[r], xd[r][v][e], acc2[v][e]);
-            else acc[v][e] = fma(mu[r], xd[r][v][e], acc[v][e]);
-          }
+          for (int e = 0; e < EPV; ++e) acc[v][e] = fma(mu[r], xd[r][v][e], acc[v][e]);
+      }
+      if (MODE == 2) {   // the gradient at w2 from the same retained tile
+#pragma unroll
+        for (int r = 0; r < R; ++r) mu[r] = mult2_s[g * R + (r ^ rperm)];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+              double &dst = accB[MODE == 2 ? v : 0][MODE == 2 ? e : 0];
+              dst = fma(mu[r], xd[r][v][e], dst);
+            }
       }
     };
     if (a.kind == AGD_GRAD_LOGISTIC && warp == sw) {
@@ -358,41 +454,43 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
       phase2();
     }
   }
-#pragma unroll
-  for (int v = 0; v < V; ++v)
-#pragma unroll
-    for (int e = 0; e < EPV; ++e) acc[v][e] += acc2[v][e];
 
-  // ---------------- per-CTA slab: column sums (row groups added in fixed order) and loss sum
+  // ---------------- per-CTA slab: column sums (row groups added in fixed order) and loss sum.  MODE 2: a second block of
+  // d + 4 doubles [gradient at w2 | loss sum | count | 0 | 0] follows the first.
   double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
-  if (NG > 1) {
-    __syncthreads();  // aux (w staging) is free for reuse: every thread read it before the loop
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int e = 0; e < EPV; ++e) aux[(size_t)g * (TPR * V * EPV) + (v * TPR + t) * EPV + e] = acc[v][e];
-    __syncthreads();
-    if (g == 0) {
+  auto write_columns = [&](double (&av)[V][EPV], double *dst) {
+    if (NG > 1) {
+      __syncthreads();  // aux (w staging) is free for reuse: every thread is past the tile loop
+      double *ax = reinterpret_cast<double *>(aux);
 #pragma unroll
       for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-          double sacc = 0.0;
-          for (int gg = 0; gg < NG; ++gg) sacc += aux[(size_t)gg * (TPR * V * EPV) + (v * TPR + t) * EPV + e];
-          acc[v][e] = sacc;
-        }
-    }
-  }
-  if (g == 0) {
+        for (int e = 0; e < EPV; ++e) ax[(size_t)g * (TPR * V * EPV) + (v * TPR + t) * EPV + e] = av[v][e];
+      __syncthreads();
+      if (g == 0) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int vec = v * TPR + t;
-      if (vec < nvec) {
+        for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) slab[vec * EPV + e] = acc[v][e];
+          for (int e = 0; e < EPV; ++e) {
+            double sacc = 0.0;
+            for (int gg = 0; gg < NG; ++gg) sacc += ax[(size_t)gg * (TPR * V * EPV) + (v * TPR + t) * EPV + e];
+            av[v][e] = sacc;
+          }
       }
     }
-  }
+    if (g == 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int vec = v * TPR + t;
+        if (vec < nvec) {
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) dst[vec * EPV + e] = av[v][e];
+        }
+      }
+    }
+  };
+  write_columns(acc, slab);
+  if (MODE == 2) write_columns(reinterpret_cast<double (&)[V][EPV]>(accB), slab + a.d + 4);
   // DUAL: lanes 16-31 hold the sums at w2.  Skipping the xor-16 step leaves the lane-0 total bit-identical to the
   // single-point kernel's, whose lanes >= 16 only ever contribute exact zeros.
   for (int off = DUAL ? 8 : 16; off >= 1; off >>= 1) {
@@ -411,257 +509,12 @@ k1_ring_kernel(const K1Args a, const int nvec, const long long ntiles, const uin
     slab[a.d + 1] = cacc;
     slab[a.d + 2] = sacc2;   // loss sum and row count at w2 (zero when the launch has no second point)
     slab[a.d + 3] = cacc2;
-  }
-}
-
-// ---------------------------------------------------------------- warp-specialised hot kernel
-// One CTA per SM: 16 consumer warps, 1 scalar warp, 1 TMA producer warp.  Consumers never meet a
-// CTA-wide barrier: step j publishes its partial dots and *arrives* on a named barrier; the scalar warp
-// turns them into loss' values while the consumers already pull and reduce step j+1; only then do the
-// consumers *sync* on the (normally long completed) result and apply phase 2 to the retained step j.
-//   named barriers: P[b] = 1 + b (512 consumer arrivals + scalar warp sync),
-//                   M[b] = 3 + b (scalar warp arrival + 512 consumer syncs),  5 = consumers only.
-constexpr int kWsConsumers = 512;
-constexpr int kWsThreads = kWsConsumers + 128;  // + one auxiliary warpgroup (scalar, producer, 2 idle)
-constexpr int kWsConsumerRegs = 104, kWsAuxRegs = 64;  // inc draws from what dec released: 128*(96-64) = 512*(104-96)
-
-__device__ __forceinline__ void named_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-struct WsLayout {
-  uint32_t stage_stride, aux_off, partial_off, mult_off, bars_off, total;
-};
-__host__ __device__ inline WsLayout ws_layout(uint32_t tile_bytes, uint32_t aux_bytes, int stages) {
-  WsLayout L;
-  L.stage_stride = round_up_u32(tile_bytes, 128);
-  L.aux_off = L.stage_stride * stages;
-  L.partial_off = L.aux_off + round_up_u32(aux_bytes, 128);
-  L.mult_off = L.partial_off + 2 * kMaxTileRows * 8 * 8;
-  L.bars_off = L.mult_off + 2 * kMaxTileRows * 8;
-  L.total = L.bars_off + (2 * stages + 1) * 8;
-  return L;
-}
-
-template <typename T, int TPR, int V, int R>
-__global__ void __launch_bounds__(kWsThreads, 1)
-k1_ws_kernel(const K1Args a, const int nvec, const long long ntiles, const uint32_t aux_bytes) {
-  constexpr int EPV = Elem<T>::EPV;
-  constexpr int NG = kWsConsumers / TPR;
-  constexpr int WPG = TPR / 32;
-  constexpr int TR = NG * R;  // rows per step
-  constexpr int NCW = kWsConsumers / 32;
-  static_assert(TR <= kMaxTileRows && WPG <= 8, "step rows");
-  extern __shared__ __align__(128) unsigned char smem[];
-
-  const int S = a.stages;
-  const uint32_t row_bytes = (uint32_t)a.d * (uint32_t)sizeof(T);
-  const WsLayout L = ws_layout(TR * row_bytes, aux_bytes, S);
-  double *aux = reinterpret_cast<double *>(smem + L.aux_off);
-  double *partial = reinterpret_cast<double *>(smem + L.partial_off);  // [2][TR][8]
-  double *mult_s = reinterpret_cast<double *>(smem + L.mult_off);      // [2][TR]
-  const uint32_t bars = smem_u32(smem + L.bars_off);  // full[s] = +8s ; empty[s] = +8(S+s) ; wbar = +16S
-  const uint32_t wbar = bars + 16u * S;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long my_steps = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  double *slab = a.slabs + (size_t)blockIdx.x * a.slab_stride;
-
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(bars + 8u * s, 1);
-      mbar_init(bars + 8u * (S + s), NCW);
-    }
-    mbar_init(wbar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  // Register re-partition (setmaxnreg): the auxiliary warpgroup gives registers back, the consumers take
-  // them.  Each role's code sits wholly inside its own branch so that ptxas allocates per role.
-  if (warp >= NCW) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsAuxRegs));
-   if (warp == NCW + 1) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(wbar, (uint32_t)a.d * 8u);
-      tma_bulk_g2s(smem_u32(aux), a.w, (uint32_t)a.d * 8u, wbar);
-      const unsigned char *Xb = reinterpret_cast<const unsigned char *>(a.X);
-      for (long long k = 0; k < my_steps; ++k) {
-        const int s = (int)(k % S);
-        const long long use = k / S;
-        if (use > 0) mbar_wait(bars + 8u * (S + s), (uint32_t)((use - 1) & 1));
-        const long long row0 = (blockIdx.x + k * (long long)gridDim.x) * TR;
-        const long long left = a.rows - row0;
-        const uint32_t rv = left < TR ? (uint32_t)left : (uint32_t)TR;
-        const uint32_t full = bars + 8u * s;
-        mbar_expect_tx(full, rv * row_bytes);
-        tma_bulk_g2s(smem_u32(smem + (size_t)s * L.stage_stride), Xb + (size_t)row0 * row_bytes, rv * row_bytes, full);
-      }
-    }
-   } else if (warp == NCW) {
-    // ===================== scalar warp: margins -> loss', loss =====================
-    double lossacc = 0.0, cntacc = 0.0;
-    double ynext = 0.0;
-    if (lane < TR) {
-      const long long r = (long long)blockIdx.x * TR + lane;
-      if (r < a.rows) ynext = a.labels[r];
-    }
-    for (long long k = 0; k < my_steps; ++k) {
-      const int b = (int)(k & 1);
-      const long long tile = blockIdx.x + k * (long long)gridDim.x;
-      const long long left = a.rows - tile * TR;
-      const int rv = left < TR ? (int)left : TR;
-      const double ylab = ynext;
-      if (lane < TR) {
-        const long long r = (tile + gridDim.x) * TR + lane;
-        if (r < a.rows) ynext = a.labels[r];
-      }
-      named_sync(1 + b, kWsConsumers + 32);  // partials of step k are in shared memory
-      if (lane < TR) {
-        const double *pp = partial + (size_t)(b * kMaxTileRows + lane) * 8;
-        double m = 0.0;
-#pragma unroll
-        for (int wi = 0; wi < WPG; ++wi) m += pp[wi];
-        double mult, loss;
-        loss_eval(a.kind, m, ylab, mult, loss);
-        const bool valid = lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + tile * TR + lane);
-        mult_s[b * kMaxTileRows + lane] = valid ? mult : 0.0;
-        lossacc += valid ? loss : 0.0;
-        cntacc += valid ? 1.0 : 0.0;
-      }
-      named_arrive(3 + b, kWsConsumers + 32);
-    }
-    for (int off = 16; off >= 1; off >>= 1) {
-      lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
-      cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
-    }
-    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; }
-   }
-    return;
-  }
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsConsumerRegs));
-
-  // ===================== consumers =====================
-  const int g = tid / TPR, t = tid % TPR, wig = t >> 5;
-  double wreg[V][EPV], acc[V][EPV];
-  mbar_wait(wbar, 0);
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    const int vec = v * TPR + t;
-#pragma unroll
-    for (int e = 0; e < EPV; ++e) {
-      wreg[v][e] = (vec < nvec) ? aux[vec * EPV + e] : 0.0;
-      acc[v][e] = 0.0;
-    }
-  }
-  double xd[2][R][V][EPV];
-
-  auto phase2 = [&](int b) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const double mu = mult_s[b * kMaxTileRows + g * R + r];
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) acc[v][e] = fma(mu, xd[b][r][v][e], acc[v][e]);
-    }
-  };
-
-  // one pipeline step on buffer B (compile-time, so xd[B] stays in registers)
-  auto step = [&](auto Bc, long long k) {
-    constexpr int B = decltype(Bc)::value;
-    const int s = (int)(k % S);
-    const uint32_t par = (uint32_t)((k / S) & 1);
-    const long long tile = blockIdx.x + k * (long long)gridDim.x;
-    const long long left = a.rows - tile * TR;
-    const int rv = left < TR ? (int)left : TR;
-    mbar_wait(bars + 8u * s, par);
-    const unsigned char *stage = smem + (size_t)s * L.stage_stride;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int vec = v * TPR + t;
-        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-        if (vec < nvec) raw = *reinterpret_cast<const uint4 *>(stage + (size_t)(g * R + r) * row_bytes + (size_t)vec * 16);
-        cvt_vec<T, EPV>(raw, xd[B][r][v]);
-      }
-    }
-    if (rv < TR) {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (g * R + r >= rv) {
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) xd[B][r][v][e] = 0.0;
-        }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bars + 8u * (S + s));  // stage may be refilled
-    double p[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) sacc = fma(xd[B][r][v][e], wreg[v][e], sacc);
-      p[r] = sacc;
-    }
-    const double tot = warp_rows_reduce<R>(p, lane);
-    if ((lane % (32 / R)) == 0) partial[(size_t)(B * kMaxTileRows + g * R + lane / (32 / R)) * 8 + wig] = tot;
-    named_arrive(1 + B, kWsConsumers + 32);
-    if (k > 0) {  // phase 2 of the previous step, whose loss' values have had a whole step to arrive
-      named_sync(3 + (B ^ 1), kWsConsumers + 32);
-      phase2(B ^ 1);
-    }
-  };
-
-  long long k = 0;
-  for (; k + 1 < my_steps; k += 2) {
-    step(std::integral_constant<int, 0>{}, k);
-    step(std::integral_constant<int, 1>{}, k + 1);
-  }
-  if (k < my_steps) {
-    step(std::integral_constant<int, 0>{}, k);
-    named_sync(3 + 0, kWsConsumers + 32);
-    phase2(0);
-  } else if (my_steps > 0) {
-    named_sync(3 + 1, kWsConsumers + 32);
-    phase2(1);
-  }
-
-  // ---------------- per-CTA slab
-  if (NG > 1) {
-    named_sync(5, kWsConsumers);
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int e = 0; e < EPV; ++e) aux[(size_t)g * (TPR * V * EPV) + (v * TPR + t) * EPV + e] = acc[v][e];
-    named_sync(5, kWsConsumers);
-    if (g == 0) {
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) {
-          double sacc = 0.0;
-          for (int gg = 0; gg < NG; ++gg) sacc += aux[(size_t)gg * (TPR * V * EPV) + (v * TPR + t) * EPV + e];
-          acc[v][e] = sacc;
-        }
-    }
-  }
-  if (g == 0) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int vec = v * TPR + t;
-      if (vec < nvec) {
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) slab[vec * EPV + e] = acc[v][e];
-      }
+    if (MODE == 2) {
+      double *slab2 = slab + a.d + 4;
+      slab2[a.d] = sacc2;
+      slab2[a.d + 1] = cacc2;
+      slab2[a.d + 2] = 0.0;
+      slab2[a.d + 3] = 0.0;
     }
   }
 }
@@ -763,20 +616,20 @@ __global__ void __launch_bounds__(256) k1_generic_kernel(const K1Args a, const l
 }
 
 // ---------------------------------------------------------------- slab reduction (combOp, AGD.scala:201-204)
-// out[c] = sum over slabs of column c, c <= d + 3 (gradient, loss sum, row count, then the same pair at the second point of a
-// fused sweep).  32 columns per block; 8 slab groups per block sum
+// out[c] = sum over slabs of column c, c < n (gradient, loss sum, row count, then the same pair at the second point of a
+// fused sweep; after a two-gradient sweep a second such block).  32 columns per block; 8 slab groups per block sum
 // strided subsets (slab b -> group b % 8) with 4 loads in flight, then group 0 adds the 8 group sums in
 // order: the summation tree is fixed, so the result is bit-reproducible.
 template <bool PUB>
-__global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int d,
+__global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict__ slabs, int blocks, int n,
                                                         double *__restrict__ out, const XchgPub pub) {
   __shared__ double part[8][33];
   __shared__ bool last;
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  const size_t stride = (size_t)d + 4;
+  const size_t stride = (size_t)n;   // n = d + 4 columns per evaluation point held by the slabs (2 (d + 4) after a two-gradient sweep)
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  if (c <= d + 3) {
+  if (c < n) {
     int b = grp;
     for (; b + 24 < blocks; b += 32) {
       const double v0 = slabs[(size_t)b * stride + c], v1 = slabs[(size_t)(b + 8) * stride + c],
@@ -787,7 +640,7 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
   }
   part[grp][cl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  if (grp == 0 && c <= d + 3) {
+  if (grp == 0 && c < n) {
     double t = 0.0;
 #pragma unroll
     for (int gi = 0; gi < 8; ++gi) t += part[gi][cl];
@@ -840,7 +693,7 @@ inline bool ring_shape(int32_t d, int elem_bytes, RingShape &sh, int &nvec) {
   return false;
 }
 
-template <typename T, int NT, int TPR, int V, int R, int MINB, bool DUAL = false>
+template <typename T, int NT, int TPR, int V, int R, int MINB, int MODE = 0>
 cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
   constexpr int EPV = Elem<T>::EPV;
   constexpr int NG = NT / TPR;
@@ -848,17 +701,19 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
   K1Args a = a_in;
   const uint32_t row_bytes = (uint32_t)a.d * sizeof(T);
   const uint32_t tile_bytes = TR * row_bytes + kMaxTileRows * 8;  // rows + their labels
-  uint32_t aux_bytes = (uint32_t)a.d * 8u;
+  // w staging: one plane set of TPR * V vectors per point; the same area later holds NG row-group partial sums
+  uint32_t aux_bytes = (uint32_t)(MODE ? 2 : 1) * TPR * V * EPV * 8u;
   if (NG > 1) {
     const uint32_t need = (uint32_t)NG * TPR * V * EPV * 8u;
     if (need > aux_bytes) aux_bytes = need;
   }
   const uint32_t budget = (227u * 1024u - MINB * 1024u) / MINB;
   int stages = a.stages > 0 ? a.stages : 4;
-  while (stages > 1 && ring_layout(tile_bytes, aux_bytes, stages, DUAL).total > budget) --stages;
+  while (stages > 1 && ring_layout(tile_bytes, aux_bytes, stages, MODE).total > budget) --stages;
   a.stages = stages;
-  const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages, DUAL);
-  auto kern = k1_ring_kernel<T, NT, TPR, V, R, MINB, DUAL>;
+  a.slab_stride = (MODE == 2 ? 2 : 1) * (a.d + 4);
+  const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages, MODE);
+  auto kern = k1_ring_kernel<T, NT, TPR, V, R, MINB, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) return e;
   const long long ntiles = (a.rows + TR - 1) / TR;
@@ -873,12 +728,13 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
 cudaError_t launch_ring_bf16(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
                              cudaStream_t st) {
   using T = __nv_bfloat16;
+  if (a.w2 && a.dual_full) return cudaErrorInvalidValue;  // the two-gradient sweep exists for fp32 / fp64 storage
   if (a.w2) {  // fused sweep: tiles of at most 16 rows
-    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 2, 2, true>(a, nvec, sm_count, blocks_out, st);
+    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 2, 2, 1>(a, nvec, sm_count, blocks_out, st);
     switch (sh.tpr) {
-      case 64: return launch_ring_inst<T, 256, 64, 1, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
-      case 128: return launch_ring_inst<T, 256, 128, 1, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
-      case 256: return launch_ring_inst<T, 256, 256, 1, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
+      case 64: return launch_ring_inst<T, 256, 64, 1, 4, 2, 1>(a, nvec, sm_count, blocks_out, st);
+      case 128: return launch_ring_inst<T, 256, 128, 1, 4, 2, 1>(a, nvec, sm_count, blocks_out, st);
+      case 256: return launch_ring_inst<T, 256, 256, 1, 4, 2, 1>(a, nvec, sm_count, blocks_out, st);
       default: return cudaErrorInvalidValue;
     }
   }
@@ -894,11 +750,17 @@ cudaError_t launch_ring_bf16(const K1Args &a, const RingShape &sh, int nvec, int
 template <typename T>
 cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
                           cudaStream_t st) {
+  if (a.w2 && a.dual_full) {  // two full evaluations per sweep (speculative sweep of the memoised pass structure)
+    if (sh.v != 1) return cudaErrorInvalidValue;   // wide threads have no registers for a second gradient
+    if (sh.tpr == 128) return launch_ring_inst<T, 256, 128, 1, 8, 2, 2>(a, nvec, sm_count, blocks_out, st);
+    if (sh.tpr == 256) return launch_ring_inst<T, 256, 256, 1, 8, 2, 2>(a, nvec, sm_count, blocks_out, st);
+    return cudaErrorInvalidValue;
+  }
   if (a.w2) {  // fused sweep: tiles of at most 16 rows
-    if (sh.v == 4) return launch_ring_inst<T, 256, 256, 4, 2, 2, true>(a, nvec, sm_count, blocks_out, st);
-    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 4, 2, true>(a, nvec, sm_count, blocks_out, st);
-    if (sh.tpr == 128) return launch_ring_inst<T, 256, 128, 1, 8, 2, true>(a, nvec, sm_count, blocks_out, st);
-    if (sh.tpr == 256) return launch_ring_inst<T, 256, 256, 1, 8, 2, true>(a, nvec, sm_count, blocks_out, st);
+    if (sh.v == 4) return launch_ring_inst<T, 256, 256, 4, 2, 2, 1>(a, nvec, sm_count, blocks_out, st);
+    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 4, 2, 1>(a, nvec, sm_count, blocks_out, st);
+    if (sh.tpr == 128) return launch_ring_inst<T, 256, 128, 1, 8, 2, 1>(a, nvec, sm_count, blocks_out, st);
+    if (sh.tpr == 256) return launch_ring_inst<T, 256, 256, 1, 8, 2, 1>(a, nvec, sm_count, blocks_out, st);
     return cudaErrorInvalidValue;
   }
   if (sh.v == 1) {
@@ -926,48 +788,6 @@ cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm
 }
 
 
-template <typename T, int TPR, int V, int R>
-cudaError_t launch_ws_inst(const K1Args &a_in, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
-  constexpr int EPV = Elem<T>::EPV;
-  constexpr int NG = kWsConsumers / TPR;
-  constexpr int TR = NG * R;
-  K1Args a = a_in;
-  const uint32_t row_bytes = (uint32_t)a.d * sizeof(T);
-  const uint32_t tile_bytes = TR * row_bytes;
-  uint32_t aux_bytes = (uint32_t)a.d * 8u;
-  const uint32_t need = (uint32_t)NG * TPR * V * EPV * 8u;
-  if (need > aux_bytes) aux_bytes = need;
-  const uint32_t budget = 227u * 1024u - 1024u;
-  int stages = a.stages > 0 ? a.stages : 6;
-  while (stages > 1 && ws_layout(tile_bytes, aux_bytes, stages).total > budget) --stages;
-  a.stages = stages;
-  const WsLayout L = ws_layout(tile_bytes, aux_bytes, stages);
-  auto kern = k1_ws_kernel<T, TPR, V, R>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-  if (e != cudaSuccess) return e;
-  const long long ntiles = (a.rows + TR - 1) / TR;
-  long long grid = sm_count;
-  if (grid > ntiles) grid = ntiles;
-  if (grid < 1) grid = 1;
-  *blocks_out = (int)grid;
-  kern<<<(unsigned)grid, kWsThreads, L.total, st>>>(a, nvec, ntiles, aux_bytes);
-  return cudaGetLastError();
-}
-
-template <typename T>
-cudaError_t launch_ws_t(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out, cudaStream_t st) {
-  if (sh.v == 1) {
-    switch (sh.tpr) {
-      case 32: return launch_ws_inst<T, 32, 1, 2>(a, nvec, sm_count, blocks_out, st);
-      case 64: return launch_ws_inst<T, 64, 1, 4>(a, nvec, sm_count, blocks_out, st);
-      case 128: return launch_ws_inst<T, 128, 1, 4>(a, nvec, sm_count, blocks_out, st);
-      default: return launch_ws_inst<T, 256, 1, 4>(a, nvec, sm_count, blocks_out, st);
-    }
-  }
-  if (sh.v == 2) return launch_ws_inst<T, 256, 2, 2>(a, nvec, sm_count, blocks_out, st);
-  return launch_ws_inst<T, 256, 4, 1>(a, nvec, sm_count, blocks_out, st);
-}
-
 }  // namespace
 
 int k1_max_blocks(int sm_count) { return 4 * sm_count; }
@@ -986,6 +806,14 @@ int k1_ring_dual_supported(int32_t d, int elem_bytes) {
   return (256 / sh.tpr) * sh.r <= 16 ? 1 : 0;
 }
 
+// ... and the two-gradient sweep for the fp32 / fp64 instantiations of those shapes
+int k1_ring_dual_full_supported(int32_t d, int elem_bytes) {
+  RingShape sh;
+  int nvec;
+  if ((elem_bytes != 4 && elem_bytes != 8) || !ring_shape(d, elem_bytes, sh, nvec)) return 0;
+  return sh.v == 1 && (sh.tpr == 128 || sh.tpr == 256) ? 1 : 0;   // one vector per thread: d <= 1024 (fp32) / 512 (fp64)
+}
+
 cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
   RingShape sh;
   int nvec = 0;
@@ -994,15 +822,6 @@ cudaError_t k1_ring_launch(const K1Args &a, int elem_bytes, int sm_count, int *b
   if (elem_bytes == 2) return launch_ring_bf16(a, sh, nvec, sm_count, blocks_out, st);
   if (elem_bytes == 4) return launch_ring_t<float>(a, sh, nvec, sm_count, blocks_out, st);
   return launch_ring_t<double>(a, sh, nvec, sm_count, blocks_out, st);
-}
-
-cudaError_t k1_ws_launch(const K1Args &a, int elem_bytes, int sm_count, int *blocks_out, cudaStream_t st) {
-  RingShape sh;
-  int nvec = 0;
-  if (elem_bytes == 2 || a.w2 || !ring_shape(a.d, elem_bytes, sh, nvec)) return cudaErrorInvalidValue;
-  if (a.rows <= 0) { *blocks_out = 0; return cudaSuccess; }
-  if (elem_bytes == 4) return launch_ws_t<float>(a, sh, nvec, sm_count, blocks_out, st);
-  return launch_ws_t<double>(a, sh, nvec, sm_count, blocks_out, st);
 }
 
 cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int max_blocks, int *blocks_out,
@@ -1020,12 +839,10 @@ cudaError_t k1_generic_launch(const K1Args &a, int elem_bytes, int sm_count, int
   return cudaGetLastError();
 }
 
-cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t d, int64_t rows, double *out, const XchgPub *pub,
-                             cudaStream_t st) {
-  (void)rows;
-  const int grid = (d + 4 + 31) / 32;
-  if (pub) k1_reduce_kernel<true><<<grid, 256, 0, st>>>(slabs, blocks, d, out, *pub);
-  else k1_reduce_kernel<false><<<grid, 256, 0, st>>>(slabs, blocks, d, out, XchgPub());
+cudaError_t k1_reduce_launch(const double *slabs, int blocks, int32_t n, double *out, const XchgPub *pub, cudaStream_t st) {
+  const int grid = (n + 31) / 32;
+  if (pub) k1_reduce_kernel<true><<<grid, 256, 0, st>>>(slabs, blocks, n, out, *pub);
+  else k1_reduce_kernel<false><<<grid, 256, 0, st>>>(slabs, blocks, n, out, XchgPub());
   return cudaGetLastError();
 }
 

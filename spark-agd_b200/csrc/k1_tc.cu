@@ -116,7 +116,23 @@ struct TcArgs {
 // RPT = 0 selects the row-per-lane consumer mapping: a warp covers all 16 rows of the tile for two adjacent 8-feature chunks,
 // so its w reads are broadcasts (one shared-memory wavefront instead of four) and each lane owns one row's partial dot.
 __host__ __device__ constexpr int tc_consumers(int rpt) { return rpt == 4 ? 256 : 512; }
-template <int RPT>
+// packed fp32 FMA (SASS FFMA2): d.{x,y} = a.{x,y} * b.{x,y} + c.{x,y}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// F32: phase 1 in fp32 (option tc_margins=f32, the default): a bf16 is the upper half of an fp32, so widening is one ALU op
+// and there is no fp64 conversion per element; products are accumulated by packed fp32 FMAs over at most 8 terms per
+// accumulator and then added into the fp64 row sums.  Margins carry ~2^-23 relative to sum |x_i w_i| (w rounded to fp32) --
+// the same class as the gradient of this kernel (bf16 x 3 split, fp32 TMEM sums).  F32 = false keeps fp64-exact margins.
+template <int RPT, bool F32>
 __global__ void __launch_bounds__(tc_consumers(RPT) + 256, 1)
 k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap3, const TcArgs a,
              const long long ntiles) {
@@ -375,6 +391,81 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     const int rq = tid >> 6;
     const int vv = tid & 63;        // 16-byte vector within the group row
     mbar_wait(wbar, 0);
+    int slot = -1;
+    uint32_t par = 1;               // ring slot and its mbarrier phase, kept incrementally
+    const int blk = vv >> 3, ch = vv & 7;
+    const bool active = vv < a.gb * 8;
+    uint32_t x_off[RPT];            // row rq + j * kSlots of a block: 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int row = rq + j * kSlots;
+      x_off[j] = (uint32_t)(blk * kBlockBytes + row * 128 + ((ch ^ (row & 7)) << 4));
+    }
+    if constexpr (F32) {
+      // one-time re-layout of w, in place through registers: fp64 (as TMA delivered it) -> fp32 PLANES.  Chunk c (8 features)
+      // keeps features 0-3 at plane0[c] and 4-7 at plane1[c] (16 bytes each), so both per-group reads of a warp are
+      // contiguous LDS.128s.  The fp64 copy is dead afterwards (the planes overwrite its first half).
+      const int nchunks = a.d / 8;
+      float4 lo4[2], hi4[2];        // d <= 4096: at most 2 chunks per consumer thread
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kConsumers;
+        if (c < nchunks) {
+          const double *src = w_s + (size_t)c * 8;
+          lo4[i] = make_float4((float)src[0], (float)src[1], (float)src[2], (float)src[3]);
+          hi4[i] = make_float4((float)src[4], (float)src[5], (float)src[6], (float)src[7]);
+        }
+      }
+      named_sync(5, kConsumers);
+      float4 *plane0 = reinterpret_cast<float4 *>(w_s), *plane1 = plane0 + nchunks;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kConsumers;
+        if (c < nchunks) { plane0[c] = lo4[i]; plane1[c] = hi4[i]; }
+      }
+      named_sync(5, kConsumers);
+      for (long long k = 0; k < my_tiles; ++k) {
+        const int bb = (int)(k & 1);
+        double pd[RPT];
+        unsigned long long acc[RPT];     // packed fp32 pair: even / odd features of this thread's chunk
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) { pd[j] = 0.0; acc[j] = 0ull; }
+        const ulonglong2 *wp0 = reinterpret_cast<const ulonglong2 *>(plane0) + vv;
+        const ulonglong2 *wp1 = reinterpret_cast<const ulonglong2 *>(plane1) + vv;
+        for (int gi = 0; gi < a.ngt; ++gi) {
+          if (++slot == RG) slot = 0;
+          if (slot == 0) par ^= 1u;
+          mbar_wait(bars + 8u * slot, par);
+          if (active && a.diag != 100) {
+            const unsigned char *gbase = smem + (uint32_t)slot * (uint32_t)group_bytes;
+            uint4 xr[RPT];
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) xr[j] = *reinterpret_cast<const uint4 *>(gbase + x_off[j]);
+            const ulonglong2 wa = *wp0, wb = *wp1;   // (w0,w1),(w2,w3) and (w4,w5),(w6,w7) as packed fp32 pairs
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+              acc[j] = ffma2(pack2(xr[j].x << 16, xr[j].x & 0xffff0000u), wa.x, acc[j]);
+              acc[j] = ffma2(pack2(xr[j].y << 16, xr[j].y & 0xffff0000u), wa.y, acc[j]);
+              acc[j] = ffma2(pack2(xr[j].z << 16, xr[j].z & 0xffff0000u), wb.x, acc[j]);
+              acc[j] = ffma2(pack2(xr[j].w << 16, xr[j].w & 0xffff0000u), wb.y, acc[j]);
+            }
+          }
+          wp0 += a.gb * 8;
+          wp1 += a.gb * 8;
+          if ((gi & 1) || gi + 1 == a.ngt) {   // at most 8 products per fp32 accumulator, then exact fp64
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+              pd[j] += (double)(__uint_as_float((uint32_t)acc[j]) + __uint_as_float((uint32_t)(acc[j] >> 32)));
+              acc[j] = 0ull;
+            }
+          }
+        }
+        const double tot = warp_rows_reduce<RPT>(pd, lane);
+        if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
+        if ((lane & (32 / RPT - 1)) == 0) partial[(bb * kKR + rq + kSlots * (lane / (32 / RPT))) * 2 + (warp & 1)] = tot;
+        named_arrive(1 + bb, kConsumers + 32);
+      }
+    } else {
     // one-time re-layout of w: within each 64-byte chunk c (8 features) swap the four 16-byte pairs j -> j ^ ((c>>1)&3)
     for (int c = tid; c < a.d / 8; c += kConsumers) {
       const int f = (c >> 1) & 3;
@@ -386,17 +477,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
       }
     }
     named_sync(5, kConsumers);
-    int slot = -1;
-    uint32_t par = 1;               // ring slot and its mbarrier phase, kept incrementally
-    const int blk = vv >> 3, ch = vv & 7;
-    const bool active = vv < a.gb * 8;
     const int sw = (lane >> 1) & 3;
-    uint32_t x_off[RPT];            // row rq + j * kSlots of a block: 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
-#pragma unroll
-    for (int j = 0; j < RPT; ++j) {
-      const int row = rq + j * kSlots;
-      x_off[j] = (uint32_t)(blk * kBlockBytes + row * 128 + ((ch ^ (row & 7)) << 4));
-    }
     for (long long k = 0; k < my_tiles; ++k) {
       const int bb = (int)(k & 1);
       double pa[RPT], pb[RPT];
@@ -436,6 +517,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
       if ((lane & (32 / RPT - 1)) == 0) partial[(bb * kKR + rq + kSlots * (lane / (32 / RPT))) * 2 + (warp & 1)] = tot;
       named_arrive(1 + bb, kConsumers + 32);
     }
+    }  // fp64 margins
     }  // column-slice mapping
   }
 
@@ -512,17 +594,21 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
   const int smem_bytes = (int)L.total + 1024;
   cudaError_t e;
   if (a.tune_rows == 1) {  // option ring_rows=1: row-per-lane consumers (broadcast w reads; measured slower)
-    e = cudaFuncSetAttribute(k1_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = cudaFuncSetAttribute(k1_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<0><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<0, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.tune_rows == 4) {  // option ring_rows=4: 256 consumers with four rows each (measured slower)
-    e = cudaFuncSetAttribute(k1_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = cudaFuncSetAttribute(k1_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<4><<<(unsigned)grid, 512, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
-  } else {  // default: 512 consumers, two rows per thread
-    e = cudaFuncSetAttribute(k1_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    k1_tc_kernel<4, false><<<(unsigned)grid, 512, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  } else if (a.tc_margins_f64) {  // option tc_margins=f64: 512 consumers, two rows per thread, fp64-exact margins
+    e = cudaFuncSetAttribute(k1_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<2><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<2, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  } else {  // default: the same mapping with fp32 phase-1 arithmetic (packed FFMA2, no fp64 conversion per element)
+    e = cudaFuncSetAttribute(k1_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    k1_tc_kernel<2, true><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   }
   return cudaGetLastError();
 }

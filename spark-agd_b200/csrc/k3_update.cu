@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kK3Threads) k3_step_kernel(const K3StepArgs a)
     a.g_y[j] = g;
     a.z[j] = z;
     a.x[j] = x;
+    // the guessed y of the NEXT iteration (:249 with its theta), formed exactly as k3_begin / k3_combine form it
+    if (a.y_spec) a.y_spec[j] = __dadd_rn(__dmul_rn(x, a.spec_ca), __dmul_rn(z, a.spec_cb));
     const double xy = __dsub_rn(x, a.y[j]);                                               // :263
     const double dx = __dsub_rn(x, xo);
     v[0] = fma(xy, xy, v[0]);

@@ -321,6 +321,19 @@ class DeviceDataset:
                                         C.byref(cnt), C.byref(loss2)), self.h)
         return loss.value, g, cnt.value, loss2.value
 
+    def smooth_two(self, gradient: Gradient, w, w2):
+        """Two complete applySmooth evaluations from ONE sweep over the shards: (loss, grad, count, loss2, grad2)."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        w2 = np.ascontiguousarray(w2, dtype=np.float64)
+        if w.shape[0] != self.d or w2.shape[0] != self.d:
+            raise ValueError("weights have the wrong dimension")
+        g, g2 = np.empty(self.d, dtype=np.float64), np.empty(self.d, dtype=np.float64)
+        loss, loss2, cnt = C.c_double(), C.c_double(), C.c_int64()
+        self._ensure_exchange()
+        N.check(N.lib().agd_smooth_two(self.h, _grad_kind(gradient), _ptr(w), _ptr(w2), C.byref(loss), _ptr(g),
+                                       C.byref(cnt), C.byref(loss2), _ptr(g2)), self.h)
+        return loss.value, g, cnt.value, loss2.value, g2
+
     def prox(self, updater: Updater, w, g, step: float, reg: float):
         """applyProjector (AGD.scala:214-222): (regVal, newWeights)."""
         w = np.ascontiguousarray(w, dtype=np.float64)
