@@ -651,14 +651,20 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
     }
   }
   if (PUB) {
-    __threadfence_system();
+    // Release: the CTA barrier orders every thread's peer stores before thread 0, whose system-scope fence is cumulative over
+    // them (one fence per block instead of one per thread: a MEMBAR.SC.SYS waits for NVLink acknowledgements).  The block that
+    // takes the last ticket has therefore observed all blocks' stores as performed and raises the epoch flag on every peer.
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(pub.ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      last = (atomicAdd(pub.ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (last) {
-      __threadfence_system();
-      if (threadIdx.x < pub.world)
+      if (threadIdx.x < pub.world) {
+        __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(&pub.peers.flag[threadIdx.x][pub.buf * pub.world + pub.my_rank]) = pub.epoch;
+      }
       if (threadIdx.x == 0) *pub.ticket = 0u;
     }
   }

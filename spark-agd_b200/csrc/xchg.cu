@@ -16,14 +16,17 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(const double *__restr
     const double v = acc[c];
     for (int p = 0; p < pub.world; ++p) pub.peers.slot[p][base + c] = v;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(pub.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();   // one cumulative system-scope fence per block (see k1_reduce_kernel)
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(pub.ticket, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (last) {
-    __threadfence_system();
-    if (threadIdx.x < pub.world)
+    if (threadIdx.x < pub.world) {
+      __threadfence_system();
       *reinterpret_cast<volatile unsigned long long *>(&pub.peers.flag[threadIdx.x][pub.buf * pub.world + pub.my_rank]) = pub.epoch;
+    }
     if (threadIdx.x == 0) *pub.ticket = 0u;
   }
 }
@@ -33,9 +36,9 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const double *xbuf, co
                                                           int buf, int n, unsigned long long epoch, double *acc_out) {
   if (threadIdx.x < world) {
     const volatile unsigned long long *f = flags + buf * world + threadIdx.x;
-    while (*f < epoch) __nanosleep(32);
+    while (*f < epoch) __nanosleep(20);
+    __threadfence_system();   // acquire: the slot data this flag guards is read (ld.cg, from L2) after the CTA barrier
   }
-  __threadfence_system();
   __syncthreads();
   for (int c = blockIdx.x * 256 + threadIdx.x; c < n; c += gridDim.x * 256) {
     double s = 0.0;

@@ -78,7 +78,7 @@ def test_T4_class_defaults(oracle, fixture_gd_input):                         # 
 
 
 def test_T5_wide_rows_one_iteration(oracle):                                  # Suite.scala:244-259
-    m, n = 10, 2000  # the reference uses n = 200000 to trip the 1 MB frame size; the arithmetic is the same
+    m, n = 10, 200000  # the suite's own size (it exists to trip Spark's 1 MB frame size with 10 x 200000 doubles)
     rows = [oracle.jrandom_doubles(idx, (m // 2) * n).reshape(m // 2, n) for idx in (0, 1)]
     X = np.concatenate(rows, axis=0)
     y = np.ones(m)
