@@ -505,7 +505,7 @@ bool dual_supported(const agd_handle *h) {
     if (s.csr) continue;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
     const int k = dense_kernel_of(h, eb);
-    if (k == 3) return false;
+    if (k == 3 && (h->tune_rows != 0 || h->tc_margins_f64)) return false;   // tcgen05: the default (fp32-margin) mapping has one
     if (k == 1 && !k1_ring_dual_supported(h->d, eb)) return false;
   }
   return h->k1_diag == 0;
@@ -576,7 +576,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     const bool tc = k1_tc_supported(d, eb) && (h->k1_variant == 0 || h->k1_variant == 4);
     if (h->k1_variant == 4 && !tc) return fail(h, "tcgen05 kernel needs bf16 storage with d %% 128 == 0 and d <= 4096 (d=%d)", d);
     if (h->k1_variant == 1 && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
-    if (a.w2 && (tc || (ring && !k1_ring_dual_supported(d, eb))))
+    if (a.w2 && ((tc && (h->tune_rows != 0 || h->tc_margins_f64)) || (!tc && ring && !k1_ring_dual_supported(d, eb))))
       return fail(h, "internal: two-point sweep requested on a kernel without one");
     if (dual_full && (tc || !ring || !k1_ring_dual_full_supported(d, eb)))
       return fail(h, "internal: two-gradient sweep requested on a kernel without one");

@@ -100,6 +100,7 @@ __host__ __device__ inline TcLayout tc_layout(int ring_groups, int group_bytes, 
 struct TcArgs {
   const double *labels;
   const double *w;
+  const double *w2;  // optional second point (loss only): pass fusion on the bf16 path (fp32-margin mapping)
   double *slabs;
   long long rows;
   int d, kind, slab_stride;
@@ -132,7 +133,9 @@ __device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
 // and there is no fp64 conversion per element; products are accumulated by packed fp32 FMAs over at most 8 terms per
 // accumulator and then added into the fp64 row sums.  Margins carry ~2^-23 relative to sum |x_i w_i| (w rounded to fp32) --
 // the same class as the gradient of this kernel (bf16 x 3 split, fp32 TMEM sums).  F32 = false keeps fp64-exact margins.
-template <int RPT, bool F32>
+// DUAL (F32 mapping only): the loss is also evaluated at a second point w2 from the same tile -- one more packed FMA per
+// feature pair in phase 1, lanes 16-31 of the scalar warp -- with bits identical to a launch of its own at w2.
+template <int RPT, bool F32, bool DUAL = false>
 __global__ void __launch_bounds__(tc_consumers(RPT) + 256, 1)
 k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap3, const TcArgs a,
              const long long ntiles) {
@@ -243,28 +246,33 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     }
    } else if (warp == kCW + 2) {
     // ===================== scalar warp =====================
+    // lanes 0-15: the tile's rows at w (loss', loss); DUAL: lanes 16-31 the same rows at w2 (loss only)
     double lossacc = 0.0, cntacc = 0.0;
     double ynext = 0.0;
-    if (lane < kKR) {
-      const long long r = (long long)blockIdx.x * kKR + lane;
+    const int srow = lane & 15;
+    const bool second = DUAL && lane >= kKR;
+    if (lane < kKR || DUAL) {
+      const long long r = (long long)blockIdx.x * kKR + srow;
       if (r < a.rows) ynext = a.labels[r];
     }
+    const double *partial2 = partial + 2 * kKR * 2;   // [2][16 rows][2] at w2 (RPT = 2 layout)
     for (long long k = 0; k < my_tiles; ++k) {
       const int bb = (int)(k & 1);
       const long long tile = blockIdx.x + k * (long long)gridDim.x;
       const long long left = a.rows - tile * kKR;
       const int rv = left < kKR ? (int)left : kKR;
       const double ylab = ynext;
-      if (lane < kKR) {
-        const long long r = (tile + gridDim.x) * kKR + lane;
+      if (lane < kKR || DUAL) {
+        const long long r = (tile + gridDim.x) * kKR + srow;
         if (r < a.rows) ynext = a.labels[r];
       }
       named_sync(1 + bb, kConsumers + 32);                     // partial dots of tile k are in shared memory
       double mult = 0.0;
-      if (lane < kKR) {
+      if (lane < kKR || second) {
         double m;
         if (RPT) {
-          m = partial[(bb * kKR + lane) * 2] + partial[(bb * kKR + lane) * 2 + 1];
+          const double *pp = second ? partial2 : partial;
+          m = pp[(bb * kKR + srow) * 2] + pp[(bb * kKR + srow) * 2 + 1];
         } else {  // one partial per consumer warp, fixed tree
           const double *pp = partial + (bb * kKR + lane) * 16;
           m = (((pp[0] + pp[1]) + (pp[2] + pp[3])) + ((pp[4] + pp[5]) + (pp[6] + pp[7]))) +
@@ -272,7 +280,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         }
         double mu, loss;
         loss_eval(a.kind, m, ylab, mu, loss);
-        if (lane < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + tile * kKR + lane)) {
+        if (srow < rv && row_selected(a.sample_seed, a.sample_thresh, a.row_base + tile * kKR + srow)) {
           mult = mu; lossacc += loss; cntacc += 1.0;
         }
       }
@@ -294,11 +302,14 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(b2_full + 8u * bb);
     }
-    for (int off = 16; off >= 1; off >>= 1) {
+    // DUAL: skipping the xor-16 step keeps the lane-0 / lane-16 totals bit-identical to a one-point launch at either point
+    // (whose lanes >= 16 only ever contribute exact zeros)
+    for (int off = DUAL ? 8 : 16; off >= 1; off >>= 1) {
       lossacc += __shfl_xor_sync(0xffffffffu, lossacc, off);
       cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
     }
-    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; }
+    if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; if (!DUAL) { slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; } }
+    if (DUAL && lane == kKR) { slab[a.d + 2] = lossacc; slab[a.d + 3] = cntacc; }
    }
   } else if (warp >= kCW + 4) {
     // ===================== flush warpgroup: owns the fp64 gradient, drains TMEM every kFlush tiles ==========
@@ -406,7 +417,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
       // keeps features 0-3 at plane0[c] and 4-7 at plane1[c] (16 bytes each), so both per-group reads of a warp are
       // contiguous LDS.128s.  The fp64 copy is dead afterwards (the planes overwrite its first half).
       const int nchunks = a.d / 8;
-      float4 lo4[2], hi4[2];        // d <= 4096: at most 2 chunks per consumer thread
+      float4 lo4[2], hi4[2], lo4b[2], hi4b[2];   // d <= 4096: at most 2 chunks per consumer thread
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = tid + i * kConsumers;
@@ -414,24 +425,37 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
           const double *src = w_s + (size_t)c * 8;
           lo4[i] = make_float4((float)src[0], (float)src[1], (float)src[2], (float)src[3]);
           hi4[i] = make_float4((float)src[4], (float)src[5], (float)src[6], (float)src[7]);
+          if (DUAL) {   // w2 comes straight from global memory (L2): once per CTA
+            const double *s2 = a.w2 + (size_t)c * 8;
+            lo4b[i] = make_float4((float)s2[0], (float)s2[1], (float)s2[2], (float)s2[3]);
+            hi4b[i] = make_float4((float)s2[4], (float)s2[5], (float)s2[6], (float)s2[7]);
+          }
         }
       }
       named_sync(5, kConsumers);
+      // planes of w in the first half of the staging area, of w2 in the second half (the fp64 copy of w is dead by now)
       float4 *plane0 = reinterpret_cast<float4 *>(w_s), *plane1 = plane0 + nchunks;
+      float4 *plane0b = plane1 + nchunks, *plane1b = plane0b + nchunks;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int c = tid + i * kConsumers;
-        if (c < nchunks) { plane0[c] = lo4[i]; plane1[c] = hi4[i]; }
+        if (c < nchunks) {
+          plane0[c] = lo4[i]; plane1[c] = hi4[i];
+          if (DUAL) { plane0b[c] = lo4b[i]; plane1b[c] = hi4b[i]; }
+        }
       }
       named_sync(5, kConsumers);
+      double *partial2 = partial + 2 * kKR * 2;
       for (long long k = 0; k < my_tiles; ++k) {
         const int bb = (int)(k & 1);
-        double pd[RPT];
-        unsigned long long acc[RPT];     // packed fp32 pair: even / odd features of this thread's chunk
+        double pd[RPT], pd2[RPT];
+        unsigned long long acc[RPT], acc2[RPT];     // packed fp32 pair: even / odd features of this thread's chunk
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) { pd[j] = 0.0; acc[j] = 0ull; }
+        for (int j = 0; j < RPT; ++j) { pd[j] = 0.0; acc[j] = 0ull; pd2[j] = 0.0; acc2[j] = 0ull; }
         const ulonglong2 *wp0 = reinterpret_cast<const ulonglong2 *>(plane0) + vv;
         const ulonglong2 *wp1 = reinterpret_cast<const ulonglong2 *>(plane1) + vv;
+        const ulonglong2 *wq0 = reinterpret_cast<const ulonglong2 *>(plane0b) + vv;
+        const ulonglong2 *wq1 = reinterpret_cast<const ulonglong2 *>(plane1b) + vv;
         for (int gi = 0; gi < a.ngt; ++gi) {
           if (++slot == RG) slot = 0;
           if (slot == 0) par ^= 1u;
@@ -442,27 +466,48 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < RPT; ++j) xr[j] = *reinterpret_cast<const uint4 *>(gbase + x_off[j]);
             const ulonglong2 wa = *wp0, wb = *wp1;   // (w0,w1),(w2,w3) and (w4,w5),(w6,w7) as packed fp32 pairs
+            ulonglong2 va = wa, vb = wb;
+            if (DUAL) { va = *wq0; vb = *wq1; }
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
-              acc[j] = ffma2(pack2(xr[j].x << 16, xr[j].x & 0xffff0000u), wa.x, acc[j]);
-              acc[j] = ffma2(pack2(xr[j].y << 16, xr[j].y & 0xffff0000u), wa.y, acc[j]);
-              acc[j] = ffma2(pack2(xr[j].z << 16, xr[j].z & 0xffff0000u), wb.x, acc[j]);
-              acc[j] = ffma2(pack2(xr[j].w << 16, xr[j].w & 0xffff0000u), wb.y, acc[j]);
+              const unsigned long long x0 = pack2(xr[j].x << 16, xr[j].x & 0xffff0000u), x1 = pack2(xr[j].y << 16, xr[j].y & 0xffff0000u),
+                                       x2 = pack2(xr[j].z << 16, xr[j].z & 0xffff0000u), x3 = pack2(xr[j].w << 16, xr[j].w & 0xffff0000u);
+              acc[j] = ffma2(x0, wa.x, acc[j]);
+              acc[j] = ffma2(x1, wa.y, acc[j]);
+              acc[j] = ffma2(x2, wb.x, acc[j]);
+              acc[j] = ffma2(x3, wb.y, acc[j]);
+              if (DUAL) {
+                acc2[j] = ffma2(x0, va.x, acc2[j]);
+                acc2[j] = ffma2(x1, va.y, acc2[j]);
+                acc2[j] = ffma2(x2, vb.x, acc2[j]);
+                acc2[j] = ffma2(x3, vb.y, acc2[j]);
+              }
             }
           }
           wp0 += a.gb * 8;
           wp1 += a.gb * 8;
+          wq0 += a.gb * 8;
+          wq1 += a.gb * 8;
           if ((gi & 1) || gi + 1 == a.ngt) {   // at most 8 products per fp32 accumulator, then exact fp64
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
               pd[j] += (double)(__uint_as_float((uint32_t)acc[j]) + __uint_as_float((uint32_t)(acc[j] >> 32)));
               acc[j] = 0ull;
+              if (DUAL) {
+                pd2[j] += (double)(__uint_as_float((uint32_t)acc2[j]) + __uint_as_float((uint32_t)(acc2[j] >> 32)));
+                acc2[j] = 0ull;
+              }
             }
           }
         }
         const double tot = warp_rows_reduce<RPT>(pd, lane);
+        double tot2 = 0.0;
+        if (DUAL) tot2 = warp_rows_reduce<RPT>(pd2, lane);
         if (k >= 2) named_sync(3 + bb, kConsumers + 32);         // scalar warp is done with partial[bb] of tile k-2
-        if ((lane & (32 / RPT - 1)) == 0) partial[(bb * kKR + rq + kSlots * (lane / (32 / RPT))) * 2 + (warp & 1)] = tot;
+        if ((lane & (32 / RPT - 1)) == 0) {
+          partial[(bb * kKR + rq + kSlots * (lane / (32 / RPT))) * 2 + (warp & 1)] = tot;
+          if (DUAL) partial2[(bb * kKR + rq + kSlots * (lane / (32 / RPT))) * 2 + (warp & 1)] = tot2;
+        }
         named_arrive(1 + bb, kConsumers + 32);
       }
     } else {
@@ -571,7 +616,8 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
   TcArgs t;
   t.one_copy = a.tune_ctas == 2 ? 0 : 1;   // option ring_ctas=2: one 2-D copy per 64-feature block (slower: 8x the TMA operations)
   t.diag = (a.kind == 100 || a.kind == 101) ? a.kind : 0;
-  t.labels = a.labels; t.w = a.w; t.slabs = a.slabs; t.rows = a.rows; t.d = a.d; t.kind = a.kind;
+  if (a.w2 && (a.tune_rows != 0 || a.tc_margins_f64)) return cudaErrorInvalidValue;   // two-point form: default mapping only
+  t.labels = a.labels; t.w = a.w; t.w2 = a.w2; t.slabs = a.slabs; t.rows = a.rows; t.d = a.d; t.kind = a.kind;
   t.slab_stride = a.slab_stride;
   t.sample_seed = a.sample_seed; t.sample_thresh = a.sample_thresh; t.row_base = a.row_base;
   const int nblk = a.d / 64;
@@ -605,6 +651,10 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
     e = cudaFuncSetAttribute(k1_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     k1_tc_kernel<2, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  } else if (a.w2) {  // the default mapping + the loss at a second point (pass fusion)
+    e = cudaFuncSetAttribute(k1_tc_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    k1_tc_kernel<2, true, true><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else {  // default: the same mapping with fp32 phase-1 arithmetic (packed FFMA2, no fp64 conversion per element)
     e = cudaFuncSetAttribute(k1_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;

@@ -492,7 +492,8 @@ def test_suite_T5_wide_rows(agd, ctx, oracle):                                  
 PAIR_SHAPES = [((3001, 1024), "f32", "auto"), ((2000, 512), "f32", "auto"), ((501, 1001), "f32", "auto"),
                ((777, 2048), "f32", "auto"), ((300, 4096), "f32", "auto"), ((1500, 512), "f64", "auto"),
                ((400, 2048), "f64", "auto"), ((10, 20000), "f32", "auto"), ((700, 300), "f64", "generic"),
-               ((2000, 1024), "bf16", "ring"), ((900, 2048), "bf16", "ring"), ((600, 4096), "bf16", "ring")]
+               ((2000, 1024), "bf16", "ring"), ((900, 2048), "bf16", "ring"), ((600, 4096), "bf16", "ring"),
+               ((2000, 1024), "bf16", "tc"), ((517, 4096), "bf16", "tc"), ((300, 128), "bf16", "tc")]
 
 
 @pytest.mark.parametrize("grad", GRADS)
@@ -609,7 +610,8 @@ def test_smooth_pair_csr_and_unsupported_kernels(agd, ctx, oracle):
     # kernels without a two-point form refuse (agd_run then simply does not fuse)
     X = rng.standard_normal((300, 1024)).astype(np.float32)
     yd = (rng.random(300) > 0.5).astype(np.float64)
-    ds = ctx.parallelize(yd, X, store="bf16")                   # tcgen05 path
+    ds = ctx.parallelize(yd, X, store="bf16")                   # tcgen05 path: only its default (fp32-margin) mapping has one
+    ds.set_option("tc_margins", "f64")
     with pytest.raises(agd.NativeError, match="two-point"):
         ds.smooth_pair(agd.LogisticGradient(), np.zeros(1024), np.zeros(1024))
     ds.close()
@@ -627,7 +629,10 @@ FUSE_CASES = [(20000, 1024, "logistic", "simple", 0.0, "f32", 12, {}),
               (4000, 2048, "least_squares", "simple", 0.0, "f64", 25, {"L0": 1e-3}),          # L-increase branch
               (4000, 300, "logistic", "simple", 0.0, "f64", 20, {"beta": 1.0, "L0": 0.25, "Lexact": 0.25, "may_restart": False}),
               (3000, 20000, "logistic", "squared_l2", 0.01, "f32", 8, {}),                    # generic kernel
-              (1000, 512, "least_squares", "simple", 0.0, "f64", 60, {"tol": 1e-6})]          # leaves through :322-324
+              (1000, 512, "least_squares", "simple", 0.0, "f64", 60, {"tol": 1e-6}),          # leaves through :322-324
+              (6000, 1024, "least_squares", "squared_l2", 0.01, "bf16", 10,                     # tcgen05 kernel, branch-free config
+               {"beta": 1.0, "L0": 8.0, "Lexact": 8.0, "may_restart": False}),
+              (5000, 4096, "logistic", "simple", 0.0, "bf16", 8, {})]                           # tcgen05 kernel, defaults
 
 
 @pytest.mark.parametrize("case", FUSE_CASES, ids=[f"{c[0]}x{c[1]}-{c[2]}-{c[3]}-{i}" for i, c in enumerate(FUSE_CASES)])
@@ -636,7 +641,7 @@ def test_fused_run_is_bit_identical_to_unfused(agd, ctx, case):
     same evaluations, same weights and loss history bit for bit, one sweep over X fewer per iteration."""
     n, d, grad, upd, reg, store, iters, kw = case
     rng = np.random.default_rng(n + d + iters + 9)
-    X, y = make_data(rng, n, d, grad, np.float32 if store == "f32" else np.float64)
+    X, y = make_data(rng, n, d, grad, np.float64 if store == "f64" else np.float32)
     data = ctx.parallelize(y, X, store=store)
     args = (data, G(agd, grad), U(agd, upd), kw.get("tol", 0.0), iters, reg, np.zeros(d), kw.get("L0", 1.0),
             kw.get("Lexact", float("inf")), kw.get("beta", 0.5), kw.get("alpha", 0.9), kw.get("may_restart", True))
