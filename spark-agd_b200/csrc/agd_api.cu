@@ -74,8 +74,6 @@ struct Shard {
   int32_t *idx = nullptr;
   void *val = nullptr;
   int64_t nnz = 0, nnz_cap = 0;
-  CsrTiles tiles;             // column-blocked, row-tiled twin (k1_csr_tiles.cu), built on first use after a load
-  bool tiles_valid = false;
 };
 
 struct Dev {
@@ -127,7 +125,6 @@ struct agd_handle {
   int tune_rows = 0, tune_ctas = 0, tune_full = 0;
   int k1_diag = 0;
   int tc_margins_f64 = 0;    // tcgen05 kernel: fp64-exact margins instead of the fp32 phase 1
-  int csr_format = 0;        // 0 = auto (tiles for shards of >= 4M stored entries), 1 = row-major kernel, 2 = tiled kernel
   unsigned long long sample_seed = 0, sample_thresh = 0;  // mini-batch row mask of the current pass (0 = every row)
   int collective = 0;        // 0 = auto (peer memory if every pair of ranks can map each other, else NCCL), 1 = nccl, 2 = p2p
   int32_t x_d = 0;           // dimension the exchange buffers were built for (0 = not built)
@@ -192,7 +189,6 @@ int free_shard(agd_handle *h, Dev &D) {
   if (s.rowptr) cudaFree(s.rowptr);
   if (s.idx) cudaFree(s.idx);
   if (s.val) cudaFree(s.val);
-  csr_tiles_free(&s.tiles);
   s = Shard();
   return 0;
 }
@@ -549,16 +545,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
       a.w2 = w2_of ? w2_of(D) : nullptr;
       a.gacc = D.acc; a.rows = s.rows; a.d = d; a.kind = kind;
       a.sample_seed = h->sample_seed; a.sample_thresh = h->sample_thresh; a.row_base = D.row_base; a.tune = h->tune_rows;
-      const bool tiled = h->csr_format == 2 || (h->csr_format == 0 && s.nnz >= (4LL << 20));
-      if (tiled && !s.tiles_valid) {   // (re)build the tiled twin: once per load, outside any timed region that matters
-        Shard &sm = D.sh;
-        csr_tiles_free(&sm.tiles);
-        CK(csr_tiles_build(s.rowptr, s.idx, s.val, s.elem_bytes, s.rows, s.nnz, d, D.sm_count, &sm.tiles, D.st));
-        sm.tiles_valid = true;
-      }
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-      if (tiled) CK(k1_csr_tiles_launch(a, s.tiles, s.elem_bytes, D.sm_count, D.st));
-      else CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
+      CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
       if (p2p) { const XchgPub pub = make_pub(D, i); CK(xchg_publish_launch(D.acc, pub, D.st)); }
       h->launches += (i == 0) ? (p2p ? 3 : 2) : 0;
@@ -1037,7 +1025,6 @@ int agd_load_csr(agd_handle *h, int32_t dev, const int64_t *rowptr, const int32_
   CK(cudaStreamSynchronize(D.st));
   s.rows = need_rows;
   s.nnz = need_nnz;
-  s.tiles_valid = false;   // the tiled twin is rebuilt on the next sweep
   return 0;
 }
 
@@ -1063,7 +1050,6 @@ int agd_generate_csr(agd_handle *h, int64_t total_rows, int32_t d, int32_t nnz_p
                         nnz_per_row, D.st));
     D.sh.rows = hi - lo;
     D.sh.nnz = (hi - lo) * nnz_per_row;
-    D.sh.tiles_valid = false;
   }
   for (Dev &D : h->devs) { CK(cudaSetDevice(D.ordinal)); CK(cudaStreamSynchronize(D.st)); }
   return 0;
@@ -1170,11 +1156,7 @@ int agd_synth_wtrue(agd_handle *h, uint64_t seed, int32_t d, double *w_out) {
 const char *agd_kernel_name(const agd_handle *h, int32_t dev) {
   if (!h || dev < 0 || dev >= (int)h->devs.size() || h->d <= 0) return "";
   const Shard &s = h->devs[dev].sh;
-  if (s.csr) {
-    const bool tiled = h->csr_format == 2 || (h->csr_format == 0 && s.nnz >= (4LL << 20));
-    if (tiled) return s.elem_bytes == 8 ? "csr_tile_margin_kernel<double> + csr_tile_grad_kernel<double>" : "csr_tile_margin_kernel<float> + csr_tile_grad_kernel<float>";
-    return s.elem_bytes == 8 ? "k1_csr_pipelined_kernel<double>" : "k1_csr_pipelined_kernel<float>";
-  }
+  if (s.csr) return s.elem_bytes == 8 ? "k1_csr_pipelined_kernel<double>" : "k1_csr_pipelined_kernel<float>";
   const int eb = s.elem_bytes ? s.elem_bytes : 4;
   const char *t = eb == 8 ? "double" : (eb == 4 ? "float" : "__nv_bfloat16");
   static thread_local char buf[96];
@@ -1205,13 +1187,6 @@ int agd_set_option(agd_handle *h, const char *key, const char *value) {
     return 0;
   }
   if (!strcmp(key, "k1_diag")) { h->k1_diag = atoi(value); return 0; }
-  if (!strcmp(key, "csr_format")) {
-    if (!strcmp(value, "auto")) h->csr_format = 0;
-    else if (!strcmp(value, "rows")) h->csr_format = 1;
-    else if (!strcmp(value, "tiles")) h->csr_format = 2;
-    else return fail(h, "csr_format must be auto|rows|tiles");
-    return 0;
-  }
   if (!strcmp(key, "tc_margins")) {
     if (!strcmp(value, "f32")) h->tc_margins_f64 = 0;
     else if (!strcmp(value, "f64")) h->tc_margins_f64 = 1;

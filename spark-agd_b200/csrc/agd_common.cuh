@@ -84,20 +84,6 @@ struct K1CsrArgs {
 };
 cudaError_t k1_csr_launch(const K1CsrArgs &a, int elem_bytes, int sm_count, cudaStream_t st);
 
-// Column-blocked, row-tiled twin of a CSR shard (k1_csr_tiles.cu): entries re-ordered at load time into (65536-row tile) x
-// (8192-column block) tiles so that the column-indexed side of both contractions (w gather, g scatter) lives in shared memory.
-struct CsrTiles {
-  uint32_t *pk = nullptr;        // [nnz] (local row << 13) | local column
-  void *tval = nullptr;          // [nnz] values in tile order (float or double)
-  long long *tile_ptr = nullptr; // [ntiles + 1]
-  double *m = nullptr, *m2 = nullptr, *mult = nullptr;   // per-row margins (two points) and loss' (rows padded to whole tiles)
-  int nb = 0;                    // column blocks
-  long long nrt = 0, ntiles = 0, nnz = 0, rows = 0;
-};
-cudaError_t csr_tiles_build(const int64_t *rowptr, const int32_t *idx, const void *val, int elem_bytes, int64_t rows, int64_t nnz,
-                            int32_t d, int sm_count, CsrTiles *out, cudaStream_t st);
-void csr_tiles_free(CsrTiles *t);
-cudaError_t k1_csr_tiles_launch(const K1CsrArgs &a, const CsrTiles &t, int elem_bytes, int sm_count, cudaStream_t st);
 
 // ---------------------------------------------------------------- K3: fused O(d) driver-side vector work
 // Replaces the breeze d-vector ops of AGD.scala:249,255,263-264,273,278,315-316,327, the

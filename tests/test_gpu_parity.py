@@ -298,56 +298,6 @@ def test_csr_smooth_matches_oracle(agd, ctx, oracle, grad, store):
     loss1, g1, _ = ds.smooth(G(agd, grad), w)
     np.testing.assert_allclose(loss1, loss, rtol=1e-14)   # same per-row arithmetic; only the order of the atomic sums differs
     assert rel_err(g1, g) < 1e-14
-    ds.set_option("csr_format", "tiles")              # the column-blocked, row-tiled twin (k1_csr_tiles.cu)
-    loss2, g2, cnt2 = ds.smooth(G(agd, grad), w)
-    assert cnt2 == n
-    np.testing.assert_allclose(loss2, ref_loss, rtol=1e-12)
-    assert rel_err(g2, ref_g) < 1e-12
-    ds.close()
-
-
-@pytest.mark.parametrize("grad,store,n,d,k", [("hinge", "f32", 140000, 20000, 8), ("logistic", "f64", 70000, 8193, 5),
-                                              ("least_squares", "f32", 65537, 1_000_000, 12), ("hinge", "f32", 3000, 7, 3)])
-def test_csr_tiled_layout_matches_oracle(agd, ctx, oracle, grad, store, n, d, k):
-    """Shards spanning several 65536-row tiles and 8192-column blocks (ragged last tile / block, d not a multiple of 2) through
-    the tiled kernels: applySmooth, the two-point form, appended partitions (tiles rebuilt), and a short AGD run."""
-    rng = np.random.default_rng(n + d)
-    idx = np.sort(np.stack([rng.choice(d, k, replace=False) for _ in range(2000)]), axis=1).astype(np.int32)
-    idx = idx[rng.integers(0, 2000, size=n)]                       # n rows drawn from 2000 distinct index patterns
-    val = rng.standard_normal((n, k)).astype(np.float32 if store == "f32" else np.float64)
-    rowptr = np.arange(n + 1, dtype=np.int64) * k
-    w_true = rng.standard_normal(d)
-    mrg = np.einsum("ij,ij->i", val.astype(np.float64), w_true[idx])
-    y = (mrg + 0.3 * rng.standard_normal(n) > 0).astype(np.float64) if grad != "least_squares" else mrg + 0.1 * rng.standard_normal(n)
-    w, w2 = rng.standard_normal(d) * 0.1, rng.standard_normal(d) * 0.1
-    D = oracle.Data(y, csr=(rowptr, idx.ravel(), val.ravel()), d=d)
-    half = n // 2
-    ds = agd.DeviceDataset(ctx)
-    ds.set_option("csr_format", "tiles")
-    ds.load_csr(y[:half], rowptr[:half + 1], idx[:half].ravel(), val[:half].ravel(), d, store=store)
-    l_half = ds.smooth(G(agd, grad), w)
-    r_half = oracle.smooth(oracle.Data(y[:half], csr=(rowptr[:half + 1], idx[:half].ravel(), val[:half].ravel()), d=d), grad, w)
-    np.testing.assert_allclose(l_half[0], r_half[0], rtol=1e-12)
-    ds.load_csr(y[half:], rowptr[half:] - rowptr[half], idx[half:].ravel(), val[half:].ravel(), d, store=store)   # append: tiles rebuilt
-    loss, g, cnt = ds.smooth(G(agd, grad), w)
-    ref_loss, ref_g, _ = oracle.smooth(D, grad, w, partitions=4, threads=4)
-    assert cnt == n
-    np.testing.assert_allclose(loss, ref_loss, rtol=1e-12)
-    assert rel_err(g, ref_g) < 1e-12
-    lp, gp, cp, l2 = ds.smooth_pair(G(agd, grad), w, w2)
-    ref2 = oracle.smooth(D, grad, w2, partitions=4, threads=4)
-    np.testing.assert_allclose([lp, l2], [ref_loss, ref2[0]], rtol=1e-12)
-    assert rel_err(gp, ref_g) < 1e-12
-    ds.set_option("csr_format", "rows")                            # the row-major kernel on the same shard
-    lr, gr, _ = ds.smooth(G(agd, grad), w)
-    np.testing.assert_allclose(lr, loss, rtol=1e-13)
-    assert rel_err(gr, g) < 1e-13
-    ds.set_option("csr_format", "tiles")
-    wg, hist, st = agd.run_with_stats(ds, G(agd, grad), agd.SquaredL2Updater(), 0.0, 5, 0.05, np.zeros(d))
-    ref = oracle.agd_run(D, grad, "squared_l2", np.zeros(d), convergence_tol=0.0, num_iterations=5, reg_param=0.05,
-                         partitions=4, threads=4)
-    np.testing.assert_allclose(hist, ref.loss_history, rtol=1e-10)
-    assert rel_err(wg, ref.weights) < 1e-8
     ds.close()
 
 

@@ -9,8 +9,6 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 64
 ds = S.Context(devices=[0]).synthetic_csr(rows, d, k, S.HingeGradient(), seed=42, store="f32")
-if len(sys.argv) > 4:
-    ds.set_option("csr_format", sys.argv[4])          # rows | tiles
 w = np.random.default_rng(0).standard_normal(d) * 0.01
 for _ in range(4):
     loss, g, cnt = ds.smooth(S.HingeGradient(), w)
