@@ -315,7 +315,8 @@ def run_b200(args):
     value = total_rows * st.passes / dev_s
     # the bit-identical memoised pass structure (AGD_FLAG_MEMOIZE_FX), reported beside the headline
     barrier()
-    _, _, st_m = run(data, args.steps, memoize=True)
+    w_m, hist_m, st_m = run(data, args.steps, memoize=True)
+    memo_same = bool(np.array_equal(w_m, w) and np.array_equal(hist_m, hist))
     dev_s_m = max_over_ranks(st_m.device_ms_total / 1e3)
     # every evaluation as a sweep of its own (AGD_FLAG_NO_FUSE): the same results bit for bit, one more read of X per iteration
     barrier()
@@ -389,6 +390,11 @@ def run_b200(args):
                         "note": "AGD_FLAG_NO_FUSE: same weights and history bit for bit, 3 + 2b reads of X per iteration"},
             "memoized": {"iters_per_sec": st_m.iterations / dev_s_m, "passes_per_iter": st_m.passes / st_m.iterations,
                          "examples_per_sec": total_rows * st_m.passes / dev_s_m, "sweeps": int(st_m.k1_launches),
+                         "fused_passes": int(st_m.fused_passes), "wasted_passes": int(st_m.wasted_passes),
+                         "weights_and_history_bit_identical_to_default": memo_same,
+                         "k1_ms_per_launch": st_m.k1_ms_total / max(st_m.k1_launches, 1),
+                         "allreduce_ms_per_pass": st_m.allreduce_ms_total / max(st_m.collective_calls, 1),
+                         "device_ms": dev_s_m * 1e3, "host_wall_ms": st_m.seconds_total * 1e3,
                          "note": "AGD_FLAG_MEMOIZE_FX: same weights and history bit for bit, fewer passes"},
             "allreduce_ms_per_pass": st.allreduce_ms_total / max(st.collective_calls, 1),
             "host_wall_s": st.seconds_total, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity,

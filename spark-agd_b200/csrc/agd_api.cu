@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <limits>
@@ -132,6 +133,7 @@ struct agd_handle {
   unsigned long long x_epoch = 0;
   std::string err;
   std::mutex mu;
+  unsigned long long seq_base = 0;   // last round sequence number handed out (wait_scalars)
   int64_t launches = 0;  // per device, current call
   int64_t collectives = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -530,7 +532,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
   auto make_pub = [&](Dev &D, size_t i) {
     XchgPub pub;
     pub.peers = D.xpeers; pub.world = h->world; pub.my_rank = h->first_rank + (int)i; pub.buf = (int)(epoch & 1ull);
-    pub.n = n; pub.epoch = epoch; pub.ticket = D.xticket;
+    pub.n = n; pub.slot_stride = 2 * (d + 4); pub.epoch = epoch; pub.ticket = D.xticket;
     return pub;
   };
   for (size_t i = 0; i < h->devs.size(); ++i) {
@@ -590,7 +592,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     for (Dev &D : h->devs) {
       CK(cudaSetDevice(D.ordinal));
-      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, epoch, D.acc, D.st));
+      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, 2 * (d + 4), epoch, D.acc, D.st));
     }
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     h->launches += 1;
@@ -613,6 +615,26 @@ int read_scalars(agd_handle *h, double *out) {
   Dev &D = h->devs[0];
   CK(cudaSetDevice(D.ordinal));
   CK(cudaStreamSynchronize(D.st));  // the kernel's zero-copy stores are visible once the stream has drained
+  memcpy(out, D.scalars_host, K3_NS * sizeof(double));
+  return 0;
+}
+
+// The same without draining the stream: the last K3 kernel of a round stores `seq` behind its scalars in mapped pinned memory
+// (after a system-scope fence); the host polls that word.  No driver call sits between the kernel's last store and the host
+// loop continuing, and the stream may already hold later work.  A stream query every few thousand polls catches errors.
+int wait_scalars(agd_handle *h, unsigned long long seq, double *out) {
+  Dev &D = h->devs[0];
+  volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(D.scalars_host + 2 * K3_NS);
+  unsigned int spins = 0;
+  while (*flag != seq) {
+    if ((++spins & 0x3fffu) == 0) {
+      CK(cudaSetDevice(D.ordinal));
+      const cudaError_t q = cudaStreamQuery(D.st);
+      if (q == cudaSuccess) { if (*flag != seq) return fail(h, "internal: the round's scalars never arrived"); break; }
+      if (q != cudaErrorNotReady) return fail(h, "stream failed while waiting for a round: %s", cudaGetErrorString(q));
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
   memcpy(out, D.scalars_host, K3_NS * sizeof(double));
   return 0;
 }
@@ -736,7 +758,7 @@ int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
     if (cudaSetDevice(D.ordinal) != cudaSuccess || cudaStreamCreateWithFlags(&D.st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMalloc(&D.ticket, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(D.ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
-        cudaHostAlloc(&D.scalars_host, 2 * K3_NS * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostAlloc(&D.scalars_host, (2 * K3_NS + 2) * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
         cudaHostGetDevicePointer((void **)&D.scalars_dev, D.scalars_host, 0) != cudaSuccess) {
       fail(h, "device %d setup failed: %s", D.ordinal, cudaGetErrorString(cudaGetLastError()));
       agd_destroy(nh);
@@ -1325,6 +1347,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   const double backtrack_tol = 1e-10;                                      // :235
   const double Lexact = p->Lexact, beta = p->beta;
   double sc[K3_NS] = {0}, sg[K3_NS] = {0};
+  unsigned long long &round_seq = h->seq_base;  // every round of every call gets a fresh sequence number
 
   auto launch_all = [&](auto fn) -> int {
     for (Dev &D : h->devs) {
@@ -1384,6 +1407,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
             a.acc = D.acc + acc_off; a.x_old = D.x_old; a.z_old = D.z_old; a.y = D.y; a.g_y = D.g_y; a.z = D.z; a.x = D.x;
             a.partials = D.partials; a.ticket = D.ticket; a.scalars = D.scalars_dev;
             a.theta = theta; a.one_minus_theta = omt; a.step = step; a.reg = p->reg_param; a.d = d; a.updater = p->updater;
+            if (!speculate) { a.seq_out = reinterpret_cast<unsigned long long *>(D.scalars_dev + 2 * K3_NS); a.seq = round_seq + 1; }
             return k3_step_launch(a, D.st);
           })) return 1;
       if (speculate) {                                                     // :269, enqueued before :265 is known
@@ -1396,10 +1420,11 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
               K3GxArgs a;
               a.acc = D.acc; a.x = D.x; a.y = D.y; a.g_y = D.g_y; a.g_x = D.g_x; a.partials = D.partials;
               a.ticket = D.ticket; a.scalars = D.scalars_dev + K3_NS; a.d = d;
+              a.seq_out = reinterpret_cast<unsigned long long *>(D.scalars_dev + 2 * K3_NS); a.seq = round_seq + 1;
               return k3_gx_launch(a, D.st);
             })) return 1;
       }
-      if (read_scalars(h, sc)) return 1;                                   // the one synchronisation of this round
+      if (wait_scalars(h, ++round_seq, sc)) return 1;                      // the one host wait of this round (no stream drain)
       memcpy(sg, H0.scalars_host + K3_NS, K3_NS * sizeof(double));
       f_y = sc[6] / sc[7];                                                 // :207
       have_fx = false;

@@ -54,12 +54,14 @@ struct XchgPeers {
 struct XchgPub {
   XchgPeers peers;
   int world, my_rank, buf, n;
+  int slot_stride;          // doubles between two ranks' slots (the buffers' capacity per slot, NOT this sweep's n: sweeps of
+                            // different payloads -- d + 4 or 2 (d + 4) -- must not move the slots of the other parity buffer)
   unsigned long long epoch;
   unsigned int *ticket;
 };
 cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStream_t st);
 cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
-                               unsigned long long epoch, double *acc_out, cudaStream_t st);
+                               int slot_stride, unsigned long long epoch, double *acc_out, cudaStream_t st);
 
 // out[c] = sum_b slabs[b][c] for c < n, n = d + 4 or 2 (d + 4) (gradient sums, loss sum, row count, loss sum and count at w2; fixed order =>
 // deterministic);
@@ -100,6 +102,8 @@ struct K3StepArgs {
   int32_t d, updater;
   double *y_spec;         // optional: y_spec = x * spec_ca + z * spec_cb, the guessed y of the next iteration (speculative sweep)
   double spec_ca, spec_cb;
+  unsigned long long *seq_out = nullptr;   // optional: launch sequence number stored behind the scalars (host polls it)
+  unsigned long long seq = 0;
 };
 cudaError_t k3_step_launch(const K3StepArgs &a, cudaStream_t st);
 struct K3GxArgs {
@@ -110,6 +114,8 @@ struct K3GxArgs {
   unsigned int *ticket;
   double *scalars;        // [0] = (x-y).(g_x-g_y), [6] = loss_sum, [7] = count
   int32_t d;
+  unsigned long long *seq_out = nullptr;
+  unsigned long long seq = 0;
 };
 cudaError_t k3_gx_launch(const K3GxArgs &a, cudaStream_t st);
 // out = a*ca + b*cb (separate roundings, as breeze does at AGD.scala:249)

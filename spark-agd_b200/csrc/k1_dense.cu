@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(256) k1_reduce_kernel(const double *__restrict
     for (int gi = 0; gi < 8; ++gi) t += part[gi][cl];
     out[c] = t;
     if (PUB) {  // compute + collective in one kernel: the result goes straight into every peer's HBM over NVLink
-      const size_t off = ((size_t)pub.buf * pub.world + pub.my_rank) * pub.n + c;
+      const size_t off = ((size_t)pub.buf * pub.world + pub.my_rank) * pub.slot_stride + c;
       for (int p = 0; p < pub.world; ++p) pub.peers.slot[p][off] = t;
     }
   }

@@ -41,9 +41,12 @@ __device__ __forceinline__ double prox_elem(int updater, double w, double g, dou
 }
 
 // block reduce NS values, write partials, last block sums partials in block order -> scalars
+// seq_out != nullptr: after the scalars have been written (they live in mapped pinned host memory), the sequence number of
+// this launch is stored behind them -- the host waits for it by polling that word instead of synchronising the stream.
 template <int NS>
 __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials, unsigned int *ticket,
-                                              double *scalars, const int (&slot)[NS]) {
+                                              double *scalars, const int (&slot)[NS],
+                                              unsigned long long *seq_out = nullptr, unsigned long long seq = 0ull) {
   __shared__ double sh[NS][kK3Threads / 32];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -72,8 +75,16 @@ __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials,
       double s = 0.0;
       for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NS + threadIdx.x];
       scalars[slot[threadIdx.x]] = s;
+      __threadfence_system();
     }
     if (threadIdx.x == 0) *ticket = 0u;
+    if (seq_out) {
+      __syncthreads();   // `last` is block-uniform
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(seq_out) = seq;
+      }
+    }
   }
 }
 
@@ -102,9 +113,10 @@ __global__ void __launch_bounds__(kK3Threads) k3_step_kernel(const K3StepArgs a)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.scalars[6] = a.acc[a.d];
     a.scalars[7] = count;
+    __threadfence_system();   // ordered before this block's ticket, hence before the last block's sequence store
   }
   const int slot[6] = {0, 1, 2, 3, 4, 5};
-  finish_reduce<6>(v, a.partials, a.ticket, a.scalars, slot);
+  finish_reduce<6>(v, a.partials, a.ticket, a.scalars, slot, a.seq_out, a.seq);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_gx_kernel(const K3GxArgs a) {
@@ -120,9 +132,10 @@ __global__ void __launch_bounds__(kK3Threads) k3_gx_kernel(const K3GxArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.scalars[6] = a.acc[a.d];
     a.scalars[7] = count;
+    __threadfence_system();
   }
   const int slot[1] = {0};
-  finish_reduce<1>(v, a.partials, a.ticket, a.scalars, slot);
+  finish_reduce<1>(v, a.partials, a.ticket, a.scalars, slot, a.seq_out, a.seq);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_prox_kernel(const K3ProxArgs a) {

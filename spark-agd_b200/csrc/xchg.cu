@@ -11,7 +11,7 @@ namespace {
 // standalone publish (the CSR path has no slab reduction to fuse it into)
 __global__ void __launch_bounds__(256) xchg_publish_kernel(const double *__restrict__ acc, const XchgPub pub) {
   __shared__ bool last;
-  const size_t base = ((size_t)pub.buf * pub.world + pub.my_rank) * pub.n;
+  const size_t base = ((size_t)pub.buf * pub.world + pub.my_rank) * pub.slot_stride;
   for (int c = blockIdx.x * 256 + threadIdx.x; c < pub.n; c += gridDim.x * 256) {
     const double v = acc[c];
     for (int p = 0; p < pub.world; ++p) pub.peers.slot[p][base + c] = v;
@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) xchg_publish_kernel(const double *__restr
 
 // wait for the W flags of this epoch, then add the W slots in rank order (identical bits on every rank)
 __global__ void __launch_bounds__(256) xchg_gather_kernel(const double *xbuf, const unsigned long long *flags, int world,
-                                                          int buf, int n, unsigned long long epoch, double *acc_out) {
+                                                          int buf, int n, int slot_stride, unsigned long long epoch,
+                                                          double *acc_out) {
   if (threadIdx.x < world) {
     const volatile unsigned long long *f = flags + buf * world + threadIdx.x;
     while (*f < epoch) __nanosleep(20);
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) xchg_gather_kernel(const double *xbuf, co
   __syncthreads();
   for (int c = blockIdx.x * 256 + threadIdx.x; c < n; c += gridDim.x * 256) {
     double s = 0.0;
-    for (int r = 0; r < world; ++r) s += __ldcg(xbuf + ((size_t)buf * world + r) * n + c);  // written remotely: bypass L1
+    for (int r = 0; r < world; ++r) s += __ldcg(xbuf + ((size_t)buf * world + r) * slot_stride + c);  // written remotely: bypass L1
     acc_out[c] = s;
   }
 }
@@ -57,10 +58,10 @@ cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStrea
 }
 
 cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
-                               unsigned long long epoch, double *acc_out, cudaStream_t st) {
+                               int slot_stride, unsigned long long epoch, double *acc_out, cudaStream_t st) {
   int grid = (n + 255) / 256;
   if (grid > 64) grid = 64;
-  xchg_gather_kernel<<<grid, 256, 0, st>>>(xbuf_local, flags_local, world, buf, n, epoch, acc_out);
+  xchg_gather_kernel<<<grid, 256, 0, st>>>(xbuf_local, flags_local, world, buf, n, slot_stride, epoch, acc_out);
   return cudaGetLastError();
 }
 

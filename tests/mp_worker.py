@@ -44,6 +44,15 @@ def main():
     wf, hist, st = S.run_with_stats(data, S.LogisticGradient(), S.SquaredL2Updater(), 0.0, 8, 0.01, np.zeros(d))
     res["run"] = {"w": wf.tolist(), "hist": hist.tolist(), "passes": st.passes, "backtracks": st.backtracks,
                   "restarts": st.restarts, "collective_kind": st.collective_kind, "collective_calls": st.collective_calls}
+    # the other pass structures exchange different payloads (d + 4 or 2 (d + 4) doubles per sweep) through the same buffers:
+    # they must give the same bits on every rank
+    wm, hm, sm = S.run_with_stats(data, S.LogisticGradient(), S.SquaredL2Updater(), 0.0, 8, 0.01, np.zeros(d), memoize=True)
+    wu, hu, su = S.run_with_stats(data, S.LogisticGradient(), S.SquaredL2Updater(), 0.0, 8, 0.01, np.zeros(d), fuse=False)
+    same = bool(np.array_equal(wm, wf) and np.array_equal(hm, hist) and np.array_equal(wu, wf) and np.array_equal(hu, hist))
+    flags = [None] * world
+    dist.all_gather_object(flags, same)
+    res["modes_bit_identical_on_every_rank"] = bool(all(flags))
+    res["memo_fused_passes"] = sm.fused_passes
     # a second dimension on the same handle: the exchange is rebuilt (export / import again under transport="ipc")
     data.unpersist()
     d2 = 260

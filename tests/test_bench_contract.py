@@ -65,6 +65,7 @@ def test_b200_arm_prints_the_contract_line():
     # the accounting of pass fusion is explicit
     assert j["sweeps"] >= j["passes"] - j["fused_passes"] and j["fused_passes"] == 3
     assert j["unfused"]["loss_history_bit_identical_to_fused"] is True and j["unfused"]["sweeps"] == j["passes"]
+    assert j["memoized"]["weights_and_history_bit_identical_to_default"] is True and j["memoized"]["sweeps"] < j["sweeps"]
     assert j["clocks"] is None or {"sm_mhz", "sm_max_mhz", "reasons"} <= set(j["clocks"])
     # the full-workload comparison with the oracle rides in the line itself (north_star: weights within 1e-5)
     p = j["parity"]

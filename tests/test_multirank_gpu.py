@@ -86,6 +86,8 @@ def test_process_per_rank_world_matches_oracle(oracle, tmp_path, transport, worl
     assert np.linalg.norm(np.array(r["w"]) - ref.weights) <= 1e-9 * np.linalg.norm(ref.weights)
     assert (r["passes"], r["backtracks"], r["restarts"]) == (ref.passes, ref.backtracks, ref.restarts)
     assert r["collective_kind"] == 1 and r["collective_calls"] > 0       # the peer-memory exchange carried every pass
+    # memoised (speculative two-gradient sweeps: twice the payload) and unfused runs: the same bits on every rank
+    assert res["modes_bit_identical_on_every_rank"] is True and res["memo_fused_passes"] > 0
     # --- another dimension on the same handle (exchange rebuilt)
     X2, y2 = make_data(3000, 260, 9)
     l2, g2, c2 = O.smooth(O.Data(y2, X=X2.astype(np.float64)), "least_squares", np.full(260, 0.01), partitions=world, threads=world)
