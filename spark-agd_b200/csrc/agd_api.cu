@@ -134,6 +134,10 @@ struct agd_handle {
   std::string err;
   std::mutex mu;
   unsigned long long seq_base = 0;   // last round sequence number handed out (wait_scalars)
+  // AGD_TRACE=1 (diagnostics): an event after every launch on device 0; agd_run prints per-kernel totals (gap + run time) to stderr
+  int trace = -1;
+  std::vector<std::pair<const char *, cudaEvent_t>> tr;
+  std::vector<cudaEvent_t> tr_pool;
   int64_t launches = 0;  // per device, current call
   int64_t collectives = 0;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -486,6 +490,37 @@ int ensure_xchg(agd_handle *h) {
   return 0;
 }
 
+void trace_mark(agd_handle *h, const char *tag) {
+  if (h->trace < 0) { const char *e = getenv("AGD_TRACE"); h->trace = (e && *e && *e != '0') ? 1 : 0; }
+  if (!h->trace) return;
+  Dev &D = h->devs[0];
+  cudaSetDevice(D.ordinal);
+  cudaEvent_t ev;
+  if (h->tr.size() < h->tr_pool.size()) ev = h->tr_pool[h->tr.size()];
+  else { cudaEventCreate(&ev); h->tr_pool.push_back(ev); }
+  cudaEventRecord(ev, D.st);
+  h->tr.push_back({tag, ev});
+}
+
+void trace_report(agd_handle *h, const char *what) {
+  if (h->trace != 1 || h->tr.size() < 2) { h->tr.clear(); return; }
+  struct Acc { double ms = 0; int n = 0; };
+  std::vector<std::pair<std::string, Acc>> sums;
+  double total = 0;
+  for (size_t i = 1; i < h->tr.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->tr[i - 1].second, h->tr[i].second);
+    total += ms;
+    bool found = false;
+    for (auto &kv : sums) if (kv.first == h->tr[i].first) { kv.second.ms += ms; kv.second.n++; found = true; break; }
+    if (!found) { Acc a; a.ms = ms; a.n = 1; sums.push_back({h->tr[i].first, a}); }
+  }
+  fprintf(stderr, "[AGD_TRACE %s rank %d] total %.3f ms:", what, h->first_rank, total);
+  for (auto &kv : sums) fprintf(stderr, " %s %.3f ms / %d = %.1f us;", kv.first.c_str(), kv.second.ms, kv.second.n, kv.second.ms / kv.second.n * 1e3);
+  fprintf(stderr, "\n");
+  h->tr.clear();
+}
+
 typedef const double *(*WSel)(Dev &);
 
 // which K1 kernel a dense shard of this handle runs on (0 generic, 1 ring, 3 tcgen05)
@@ -583,8 +618,10 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     else if (ring) CK(k1_ring_launch(a, eb, D.sm_count, &blocks, D.st));
     else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
+    if (i == 0) trace_mark(h, dual_full ? "K1x2" : (w2_of ? "K1+loss" : "K1"));
     if (p2p) { const XchgPub pub = make_pub(D, i); CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, &pub, D.st)); }
     else CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, nullptr, D.st));
+    if (i == 0) trace_mark(h, p2p ? "reduce+publish" : "reduce");
     if (i == 0) h->launches += (s.rows > 0 ? 2 : 1);
   }
   if (p2p) {  // K2': every rank already holds every rank's partial sums; add them in rank order
@@ -595,6 +632,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
       CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, 2 * (d + 4), epoch, D.acc, D.st));
     }
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
+    trace_mark(h, "gather");
     h->launches += 1;
     h->collectives += 1;
   } else if (h->world > 1) {
@@ -1354,9 +1392,11 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       CK(cudaSetDevice(D.ordinal));
       CK(fn(D));
     }
+    trace_mark(h, "k3");
     h->launches += 1;
     return 0;
   };
+  trace_mark(h, "start");
 
   // Host round trips: the host needs device scalars once per backtracking round.  Pass 2 (applySmooth(x), :269) is
   // enqueued speculatively right behind pass 1 -- it is wasted only when ||x - y||^2 == 0 (:265) -- and the f_x of the
@@ -1425,6 +1465,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
             })) return 1;
       }
       if (wait_scalars(h, ++round_seq, sc)) return 1;                      // the one host wait of this round (no stream drain)
+      trace_mark(h, "host-gap");
       memcpy(sg, H0.scalars_host + K3_NS, K3_NS * sizeof(double));
       f_y = sc[6] / sc[7];                                                 // :207
       have_fx = false;
@@ -1529,6 +1570,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     CK(cudaMemcpyAsync(w_out, D.x, (size_t)h->d_user * sizeof(double), cudaMemcpyDeviceToHost, D.st));    // :337
   }
   if (call_end(h, s, t_begin)) return 1;
+  trace_report(h, memoize ? "agd_run memoised" : (fuse ? "agd_run" : "agd_run unfused"));
   for (int k = 0; k < nh; ++k)                                             // :306 for the deferred f_x values
     if (fx_deferred[(size_t)k]) loss_hist[k] = H0.hist_host[2 * (size_t)k] / H0.hist_host[2 * (size_t)k + 1] + cx_of[(size_t)k];
   *n_hist = nh;

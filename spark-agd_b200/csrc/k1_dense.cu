@@ -720,8 +720,16 @@ cudaError_t launch_ring_inst(const K1Args &a_in, int nvec, int sm_count, int *bl
   a.slab_stride = (MODE == 2 ? 2 : 1) * (a.d + 4);
   const RingLayout L = ring_layout(tile_bytes, aux_bytes, stages, MODE);
   auto kern = k1_ring_kernel<T, NT, TPR, V, R, MINB, MODE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  // the opt-in shared-memory size is a per-device property of the function: set it when it changes, not on every launch
+  static int smem_set[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || smem_set[dev] != (int)L.total) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) smem_set[dev] = (int)L.total;
+  }
   const long long ntiles = (a.rows + TR - 1) / TR;
   long long grid = (long long)MINB * sm_count;
   if (grid > ntiles) grid = ntiles;

@@ -573,6 +573,20 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
   }
 }
 
+// the opt-in shared-memory size is a per-device property of a function: set it when it changes, not on every launch
+// (one static table per call site, i.e. per kernel instantiation)
+template <int SITE, typename K>
+cudaError_t set_smem_once(K kern, int bytes) {
+  static int cur[64] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && cur[dev] == bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) cur[dev] = bytes;
+  return e;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -640,23 +654,23 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
   const int smem_bytes = (int)L.total + 1024;
   cudaError_t e;
   if (a.tune_rows == 1) {  // option ring_rows=1: row-per-lane consumers (broadcast w reads; measured slower)
-    e = cudaFuncSetAttribute(k1_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = set_smem_once<1>(k1_tc_kernel<0, false>, smem_bytes);
     if (e != cudaSuccess) return e;
     k1_tc_kernel<0, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.tune_rows == 4) {  // option ring_rows=4: 256 consumers with four rows each (measured slower)
-    e = cudaFuncSetAttribute(k1_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = set_smem_once<2>(k1_tc_kernel<4, false>, smem_bytes);
     if (e != cudaSuccess) return e;
     k1_tc_kernel<4, false><<<(unsigned)grid, 512, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.tc_margins_f64) {  // option tc_margins=f64: 512 consumers, two rows per thread, fp64-exact margins
-    e = cudaFuncSetAttribute(k1_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = set_smem_once<3>(k1_tc_kernel<2, false>, smem_bytes);
     if (e != cudaSuccess) return e;
     k1_tc_kernel<2, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.w2) {  // the default mapping + the loss at a second point (pass fusion)
-    e = cudaFuncSetAttribute(k1_tc_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = set_smem_once<4>(k1_tc_kernel<2, true, true>, smem_bytes);
     if (e != cudaSuccess) return e;
     k1_tc_kernel<2, true, true><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else {  // default: the same mapping with fp32 phase-1 arithmetic (packed FFMA2, no fp64 conversion per element)
-    e = cudaFuncSetAttribute(k1_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    e = set_smem_once<5>(k1_tc_kernel<2, true>, smem_bytes);
     if (e != cudaSuccess) return e;
     k1_tc_kernel<2, true><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   }

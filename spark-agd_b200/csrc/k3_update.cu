@@ -41,13 +41,16 @@ __device__ __forceinline__ double prox_elem(int updater, double w, double g, dou
 }
 
 // block reduce NS values, write partials, last block sums partials in block order -> scalars
-// seq_out != nullptr: after the scalars have been written (they live in mapped pinned host memory), the sequence number of
-// this launch is stored behind them -- the host waits for it by polling that word instead of synchronising the stream.
+// block reduce NS values, write partials, last block sums partials in block order -> scalars (mapped pinned host memory).
+// tail != nullptr: scalars[6..7] = tail[0..1] (loss sum, count of the evaluation the kernel consumed).
+// seq_out != nullptr: ONE thread stores every scalar, fences at system scope once, then stores the sequence number of this
+// launch behind them -- the host waits for it by polling that word instead of synchronising the stream.
 template <int NS>
 __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials, unsigned int *ticket,
-                                              double *scalars, const int (&slot)[NS],
+                                              double *scalars, const int (&slot)[NS], const double *tail = nullptr,
                                               unsigned long long *seq_out = nullptr, unsigned long long seq = 0ull) {
   __shared__ double sh[NS][kK3Threads / 32];
+  __shared__ double fin[NS];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -74,13 +77,15 @@ __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials,
     if (threadIdx.x < NS) {
       double s = 0.0;
       for (unsigned int b = 0; b < gridDim.x; ++b) s += partials[(size_t)b * NS + threadIdx.x];
-      scalars[slot[threadIdx.x]] = s;
-      __threadfence_system();
+      fin[threadIdx.x] = s;
     }
-    if (threadIdx.x == 0) *ticket = 0u;
-    if (seq_out) {
-      __syncthreads();   // `last` is block-uniform
-      if (threadIdx.x == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i) scalars[slot[i]] = fin[i];
+      if (tail) { scalars[6] = tail[0]; scalars[7] = tail[1]; }
+      *ticket = 0u;
+      if (seq_out) {
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long *>(seq_out) = seq;
       }
@@ -110,13 +115,8 @@ __global__ void __launch_bounds__(kK3Threads) k3_step_kernel(const K3StepArgs a)
     v[4] = fma(g, dx, v[4]);
     v[5] += fabs(x);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.scalars[6] = a.acc[a.d];
-    a.scalars[7] = count;
-    __threadfence_system();   // ordered before this block's ticket, hence before the last block's sequence store
-  }
   const int slot[6] = {0, 1, 2, 3, 4, 5};
-  finish_reduce<6>(v, a.partials, a.ticket, a.scalars, slot, a.seq_out, a.seq);
+  finish_reduce<6>(v, a.partials, a.ticket, a.scalars, slot, a.acc + a.d, a.seq_out, a.seq);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_gx_kernel(const K3GxArgs a) {
@@ -129,13 +129,8 @@ __global__ void __launch_bounds__(kK3Threads) k3_gx_kernel(const K3GxArgs a) {
     const double dg = __dsub_rn(g, a.g_y[j]);
     v[0] = fma(xy, dg, v[0]);                                                             // :278
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    a.scalars[6] = a.acc[a.d];
-    a.scalars[7] = count;
-    __threadfence_system();
-  }
   const int slot[1] = {0};
-  finish_reduce<1>(v, a.partials, a.ticket, a.scalars, slot, a.seq_out, a.seq);
+  finish_reduce<1>(v, a.partials, a.ticket, a.scalars, slot, a.acc + a.d, a.seq_out, a.seq);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_prox_kernel(const K3ProxArgs a) {
@@ -151,13 +146,9 @@ __global__ void __launch_bounds__(kK3Threads) k3_prox_kernel(const K3ProxArgs a)
     v[0] = fma(w, w, v[0]);
     v[1] += fabs(w);
   }
-  if (norm && blockIdx.x == 0 && threadIdx.x == 0) {
-    a.scalars[6] = a.acc_tail[0];
-    a.scalars[7] = count;
-  }
   // scalars[2] = sum w'^2, scalars[5] = sum |w'| (same slots as k3_step)
   const int slot[2] = {2, 5};
-  finish_reduce<2>(v, a.partials, a.ticket, a.scalars, slot);
+  finish_reduce<2>(v, a.partials, a.ticket, a.scalars, slot, norm ? a.acc_tail : nullptr);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_combine_kernel(double *out, const double *a, double ca,
