@@ -1,5 +1,5 @@
 """Runs a few applySmooth passes on a synthetic shard for profiling under ncu.
-usage: [AGD_PAIR=1] [AGD_OPTS=key=value,...] python tools/k1_prof.py <logistic|least_squares|hinge> [rows] [d] [store] [passes]"""
+usage: [AGD_PAIR=1 | AGD_TWO=1] [AGD_OPTS=key=value,...] python tools/k1_prof.py <logistic|least_squares|hinge> [rows] [d] [store] [passes]"""
 import os
 import sys
 
@@ -21,7 +21,9 @@ for k, v in (kv.split("=") for kv in os.environ.get("AGD_OPTS", "").split(",") i
 w = np.random.default_rng(0).standard_normal(d) * 0.02
 w2 = w + np.random.default_rng(1).standard_normal(d) * 0.01
 for _ in range(passes):
-    if os.environ.get("AGD_PAIR"):      # the fused sweep of agd_run: applySmooth at w + the loss at w2
+    if os.environ.get("AGD_TWO"):       # the speculative sweep of the memoised pass structure: two complete evaluations
+        loss, g, cnt, loss2, g2 = ds.smooth_two(grad, w, w2)
+    elif os.environ.get("AGD_PAIR"):    # the fused sweep of agd_run: applySmooth at w + the loss at w2
         loss, g, cnt, loss2 = ds.smooth_pair(grad, w, w2)
     else:
         loss, g, cnt = ds.smooth(grad, w)
