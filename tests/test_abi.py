@@ -54,6 +54,21 @@ def test_unsupported_plugins_rejected(agd):
         agd.LogisticGradient(numClasses=3)
 
 
+def test_context_transport_arguments(agd):
+    """Multi-process worlds name how the exchange is set up: NCCL ships the handles (needs the id exchange) or the host does
+    (needs the handle exchange); checked before any native call."""
+    with pytest.raises(ValueError, match="id_exchange"):
+        agd.Context(devices=[0], world_size=2, first_rank=0)
+    with pytest.raises(ValueError, match="handle_exchange"):
+        agd.Context(devices=[0], world_size=2, first_rank=0, transport="ipc")
+    with pytest.raises(ValueError, match="transport"):
+        agd.Context(devices=[0], transport="mpi")
+    c = agd.Context(devices=[0], world_size=2, first_rank=1, handle_exchange=lambda b: b + b)
+    assert c.transport == "ipc" and c.world_size == 2 and c.first_rank == 1
+    assert agd.Context(devices=[0, 1]).world_size == 2          # a single process owning several GPUs is a complete world
+    assert agd._native.ABI_VERSION == 2 and agd._native.XCHG_HANDLE_BYTES == 192
+
+
 def test_product_does_not_import_oracle():
     """The oracle is test infrastructure: nothing under the product package or include/ may reference it."""
     pkg = os.path.join(ROOT, "spark-agd_b200")

@@ -42,6 +42,27 @@ def _worker(rank, world, port, out):
         assert cnt == ref_cnt == n
         np.testing.assert_allclose(got_loss, ref_loss, rtol=1e-13)
         np.testing.assert_allclose(got_grad, ref_grad, rtol=1e-11, atol=1e-15)
+        # (3) the handle exchange closure of transport="ipc" (agd_xchg_export -> all-gather in rank order -> agd_xchg_import):
+        # every rank must end up with every rank's blob, concatenated by rank, and the slot arithmetic of the exchange
+        # (fixed stride 2 (d + 4) per rank slot, two parity buffers) must keep sweeps of both payload sizes apart
+        blob = bytes([rank]) * S._native.XCHG_HANDLE_BYTES
+        gathered = [None] * world
+        dist.all_gather_object(gathered, blob)
+        everyone = b"".join(gathered)
+        assert len(everyone) == world * S._native.XCHG_HANDLE_BYTES
+        assert all(everyone[r * S._native.XCHG_HANDLE_BYTES] == r for r in range(world))
+        stride = 2 * (d + 4)
+        spans = {}
+        for buf_i in (0, 1):
+            for r in range(world):
+                for payload in (d + 4, stride):
+                    a = (buf_i * world + r) * stride
+                    spans[(buf_i, r, payload)] = (a, a + payload)
+        for k1, (a1, b1) in spans.items():
+            for k2, (a2, b2) in spans.items():
+                if k1[:2] != k2[:2]:
+                    assert b1 <= a2 or b2 <= a1, (k1, k2)       # different (buffer, rank) slots never overlap
+            assert b1 <= 2 * world * stride                         # inside the allocation xchg_alloc makes
         out[rank] = (lo, hi)
     finally:
         dist.destroy_process_group()
