@@ -50,9 +50,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the bounded CPU sample (0 = 4M, the same at every N)")
-    ap.add_argument("--store", default="f32", choices=["f32", "bf16"],
+    ap.add_argument("--store", default="f32", choices=["f32", "bf16", "f64"],
                     help="HBM storage of the logistic_f32 workload; bf16 is the stated substitute that lets the 100M x 512 "
-                         "shape of configs[4] fit ONE GPU (204.8 GB as fp32)")
+                         "shape of configs[4] fit ONE GPU (204.8 GB as fp32); f64 is what the Scala facade stores by default "
+                         "(arbitrary Double features kept exact)")
     ap.add_argument("--parity-iters", type=int, default=10,
                     help="iterations of the full-size oracle comparison reported as `parity` (0 = off; on by default for "
                          "fp32 logistic workloads whose host copy is <= 64 GB)")
@@ -279,7 +280,7 @@ def run_b200(args):
     reg = 0.0
     if wl == "logistic_f32":
         store = args.store
-        grad, upd, eb = S.LogisticGradient(), S.SimpleUpdater(), (4 if store == "f32" else 2)
+        grad, upd, eb = S.LogisticGradient(), S.SimpleUpdater(), {"f32": 4, "bf16": 2, "f64": 8}[store]
         data = ctx.synthetic(total_rows, d, grad, seed=SEED, store=store)     # K0: never timed
     elif wl == "ls_bf16":
         grad, upd, store, eb = S.LeastSquaresGradient(), S.SimpleUpdater(), "bf16", 2
@@ -368,7 +369,7 @@ def run_b200(args):
         cpu = {k: res[k] for k in CPU_KEYS}
 
     if rank == 0:
-        wl_text = {"logistic_f32": f"logistic-loss AGD, {total_rows} x {d} dense {'fp32' if store == 'f32' else 'bf16 storage'} "
+        wl_text = {"logistic_f32": f"logistic-loss AGD, {total_rows} x {d} dense {dict(f32='fp32', bf16='bf16 storage', f64='fp64 storage')[store]} "
                                    f"({'BASELINE configs[1]' if (total_rows, d) == (10_000_000, 1024) else 'BASELINE configs[4] shape'}), "
                                    f"SimpleUpdater, w0 = 0, convergenceTol 0, defaults L0=1 beta=.5 alpha=.9 restart",
                    "ls_bf16": f"least-squares AGD, {total_rows} x {d} dense bf16 storage (BASELINE configs[3] shape), kernel {kname}",

@@ -64,7 +64,7 @@ for tag, rep, rows, d, eb in CAPTURES[ROUND]:
     summary[tag] = {"kernel": name, "rows": rows, "d": d, "metrics": m, "warp_stall_pct": stalls(rep),
                     "algorithmic_bytes": rows * (64 * (4 + eb) + 16) if csr else rows * (d * eb + 8)}
     if tag == "k1_ring_logistic_10Mx1024_f32":
-        json.dump({"kernel": "k1_ring_kernel<float,256,256,1,8,2,false>", "rows": rows, "d": d,
+        json.dump({"kernel": "k1_ring_kernel<float,256,256,1,8,2,0>" if ROUND != "r1" else "k1_ring_kernel<float,256,256,1,8,2,false>", "rows": rows, "d": d,
                    "dram_bytes_read": tobytes(m["dram__bytes_read.sum"]), "dram_bytes_write": tobytes(m["dram__bytes_write.sum"]),
                    "algorithmic_bytes": rows * (d * eb + 8), "gpu_time_ms_under_ncu": float(m["gpu__time_duration.sum"].split()[0]),
                    "source": f"ncu --set full --clock-control none, tools/k1_prof.py logistic 10000000 (round {ROUND[1:]})"},
