@@ -802,6 +802,7 @@ int agd_create(const int32_t *device_ids, int32_t n_dev, agd_handle **out) {
       agd_destroy(nh);
       return 1;
     }
+    memset(D.scalars_host, 0, (2 * K3_NS + 2) * sizeof(double));   // the sequence word behind the scalars starts at 0
   }
   nh->world = n_dev;
   nh->first_rank = 0;
