@@ -101,7 +101,8 @@ struct Dev {
   size_t ev_ar_used = 0;
   std::mutex *mu = nullptr;
   long long row_base = 0;          // global index of this shard's first row (for the sampling mask)
-  double *hist_host = nullptr;            // pinned: [2k] = loss sum, [2k+1] = count of the history pass of iteration k
+  double *hist_host = nullptr;            // pinned + mapped: [2k] = loss sum, [2k+1] = count of the history pass of iteration k
+  double *hist_dev = nullptr;             // device alias of hist_host (k3_step stores the pair that rode along with a fused sweep)
   size_t hist_cap = 0;
   // K2' peer-memory exchange (xchg.cu)
   double *xbuf = nullptr;                 // [2][W][d+4], written by every rank over NVLink
@@ -131,6 +132,10 @@ struct agd_handle {
   int32_t x_d = 0;           // dimension the exchange buffers were built for (0 = not built)
   bool x_p2p = false;        // exchange buffers are live
   unsigned long long x_epoch = 0;
+  // a sweep whose gather was left to the K3 kernel that consumes it (smooth_device(..., defer_gather))
+  bool xg_pending = false;
+  unsigned long long xg_epoch = 0;
+  int xg_n = 0;
   std::string err;
   std::mutex mu;
   unsigned long long seq_base = 0;   // last round sequence number handed out (wait_scalars)
@@ -559,7 +564,11 @@ bool dual_full_supported(const agd_handle *h) {
 // shard, slab reduction, one all-reduce of [grad | loss | count | loss2 | count2].  Result: Dev::acc on every device.
 // w2_of != nullptr: the same sweep also evaluates the loss (not the gradient) at `w2_of(dev)` -> acc[d+2], acc[d+3];
 // with dual_full also the gradient there -> a second block acc[d+4 .. 2d+7] = [grad | loss | count | 0 | 0].
-int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = nullptr, bool dual_full = false) {
+// defer_gather: on the peer-memory path the gather is left to the next K3 kernel (h->xg_pending; see XchgGather) -- one launch
+// fewer per sweep; the caller must hand the pending exchange to a k3_step / k3_gx launch before anything else reads acc.
+int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = nullptr, bool dual_full = false,
+                  bool defer_gather = false) {
+  if (h->xg_pending) return fail(h, "internal: an exchange is still waiting for its consumer");
   const int32_t d = h->d;
   const int32_t n = (dual_full ? 2 : 1) * (d + 4);   // doubles this sweep produces and exchanges
   const bool p2p = h->world > 1 && h->x_p2p;
@@ -624,7 +633,12 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     if (i == 0) trace_mark(h, p2p ? "reduce+publish" : "reduce");
     if (i == 0) h->launches += (s.rows > 0 ? 2 : 1);
   }
-  if (p2p) {  // K2': every rank already holds every rank's partial sums; add them in rank order
+  if (p2p && defer_gather) {
+    h->xg_pending = true;
+    h->xg_epoch = epoch;
+    h->xg_n = n;
+    h->collectives += 1;
+  } else if (p2p) {  // K2': every rank already holds every rank's partial sums; add them in rank order
     Dev &D0 = h->devs[0];
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     for (Dev &D : h->devs) {
@@ -698,6 +712,7 @@ int check_ready(agd_handle *h) {
 }
 
 int call_begin(agd_handle *h) {
+  h->xg_pending = false;   // a call that failed half-way may have left one behind
   Dev &D = h->devs[0];
   CK(cudaSetDevice(D.ordinal));
   if (!h->ev_begin) { CK(cudaEventCreate(&h->ev_begin)); CK(cudaEventCreate(&h->ev_end)); }
@@ -1280,6 +1295,7 @@ static int smooth_host(agd_handle *h, int32_t gradient, const double *w, const d
   }
   h->devs[0].ev_used = h->devs[0].ev_ar_used = 0;
   h->launches = h->collectives = 0;
+  h->xg_pending = false;
   if (smooth_device(h, gradient, [](Dev &D) { return (const double *)D.wtmp; }, false,
                     w2 ? (WSel)[](Dev &D) { return (const double *)D.g_x; } : (WSel) nullptr, grad2 != nullptr))
     return 1;
@@ -1408,8 +1424,19 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     CK(cudaSetDevice(H0.ordinal));
     if (H0.hist_host) cudaFreeHost(H0.hist_host);
     H0.hist_cap = 2 * (size_t)(p->num_iterations > 0 ? p->num_iterations : 1);
-    CK(cudaHostAlloc(&H0.hist_host, H0.hist_cap * sizeof(double), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&H0.hist_host, H0.hist_cap * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(cudaHostGetDevicePointer((void **)&H0.hist_dev, H0.hist_host, 0));
   }
+  // the gather of a sweep is done by the K3 kernel that consumes its sums (one launch fewer per sweep)
+  auto take_gather = [&](Dev &D) {
+    XchgGather g;
+    if (h->xg_pending) {
+      g.xbuf = D.xbuf; g.flags = D.xflags; g.world = h->world; g.buf = (int)(h->xg_epoch & 1ull); g.n = h->xg_n;
+      g.slot_stride = 2 * (d + 4); g.epoch = h->xg_epoch;
+    }
+    return g;
+  };
+  long long pending_hist = -1;        // slot of H0.hist_host the next k3_step fills from the fused sweep it consumes
   std::vector<double> cx_of;          // c_x per iteration (:305)
   std::vector<char> fx_deferred;      // f_x of iteration k still sits in H0.hist_host[2k..2k+1]
   for (int nIter = 1; nIter <= p->num_iterations; ++nIter) {              // :237
@@ -1428,7 +1455,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
         first_round = false;
       } else if (launch_all([&](Dev &D) { return k3_combine_launch(D.y, D.x_old, omt, D.z_old, theta, d, D.st); })) return 1;  // :249
       if (!y_ready) {
-        if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true)) return 1;  // :250
+        if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true, nullptr, false, true)) return 1;  // :250
         acc_off = 0;
       }
       y_ready = false;
@@ -1449,21 +1476,27 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
             a.partials = D.partials; a.ticket = D.ticket; a.scalars = D.scalars_dev;
             a.theta = theta; a.one_minus_theta = omt; a.step = step; a.reg = p->reg_param; a.d = d; a.updater = p->updater;
             if (!speculate) { a.seq_out = reinterpret_cast<unsigned long long *>(D.scalars_dev + 2 * K3_NS); a.seq = round_seq + 1; }
+            a.xg = take_gather(D); a.acc_w = D.acc;
+            a.hist_out = (pending_hist >= 0 && &D == &h->devs[0]) ? D.hist_dev + pending_hist : nullptr;
             return k3_step_launch(a, D.st);
           })) return 1;
+      h->xg_pending = false;
+      pending_hist = -1;
       if (speculate) {                                                     // :269, enqueued before :265 is known
         if (guessed) {
           if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true,
-                            [](Dev &D) { return (const double *)D.y_spec; }, true))
+                            [](Dev &D) { return (const double *)D.y_spec; }, true, true))
             return 1;
-        } else if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true)) return 1;
+        } else if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.x; }, true, nullptr, false, true)) return 1;
         if (launch_all([&](Dev &D) {
               K3GxArgs a;
               a.acc = D.acc; a.x = D.x; a.y = D.y; a.g_y = D.g_y; a.g_x = D.g_x; a.partials = D.partials;
               a.ticket = D.ticket; a.scalars = D.scalars_dev + K3_NS; a.d = d;
               a.seq_out = reinterpret_cast<unsigned long long *>(D.scalars_dev + 2 * K3_NS); a.seq = round_seq + 1;
+              a.xg = take_gather(D); a.acc_w = D.acc;
               return k3_gx_launch(a, D.st);
             })) return 1;
+        h->xg_pending = false;
       }
       if (wait_scalars(h, ++round_seq, sc)) return 1;                      // the one host wait of this round (no stream drain)
       trace_mark(h, "host-gap");
@@ -1553,13 +1586,12 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
       const double omt_n = 1.0 - theta_n;
       if (launch_all([&](Dev &D) { return k3_begin_launch(D.x_old, D.z_old, D.y, D.x, D.z, omt_n, theta_n, d, D.st); })) return 1;
       if (smooth_device(h, p->gradient, [](Dev &D) { return (const double *)D.y; }, true,
-                        [](Dev &D) { return (const double *)D.x; }))
+                        [](Dev &D) { return (const double *)D.x; }, false, true))
         return 1;
       s.passes++;          // the history evaluation; the applySmooth(y) half is counted by the next iteration
       s.fused_passes++;
       y_ready = true;
-      CK(cudaSetDevice(H0.ordinal));
-      CK(cudaMemcpyAsync(H0.hist_host + 2 * (size_t)nh, H0.acc + d + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, H0.st));
+      pending_hist = 2 * (long long)nh;   // the k3_step that consumes this sweep stores {loss sum, count} at x into the history slot
       fx_deferred.push_back(1);
       loss_hist[nh++] = 0.0;
     }
@@ -1570,6 +1602,7 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
     CK(cudaSetDevice(D.ordinal));
     CK(cudaMemcpyAsync(w_out, D.x, (size_t)h->d_user * sizeof(double), cudaMemcpyDeviceToHost, D.st));    // :337
   }
+  if (h->xg_pending || pending_hist >= 0) return fail(h, "internal: a sweep was left without its consumer");
   if (call_end(h, s, t_begin)) return 1;
   trace_report(h, memoize ? "agd_run memoised" : (fuse ? "agd_run" : "agd_run unfused"));
   for (int k = 0; k < nh; ++k)                                             // :306 for the deferred f_x values

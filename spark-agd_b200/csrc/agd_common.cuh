@@ -59,6 +59,15 @@ struct XchgPub {
   unsigned long long epoch;
   unsigned int *ticket;
 };
+// The gather half of the exchange, for kernels that consume the all-reduced sums right away (K3): instead of a launch of its own,
+// the consumer waits for the W flags, adds the W slots in rank order where it needs a value, and writes every one of the n sums
+// to `acc` for later readers.  world == 0: nothing pending, read `acc` as usual.
+struct XchgGather {
+  const double *xbuf = nullptr;               // this device's exchange buffer [2][W][slot_stride]
+  const unsigned long long *flags = nullptr;  // [2][W]
+  int world = 0, buf = 0, n = 0, slot_stride = 0;
+  unsigned long long epoch = 0;
+};
 cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStream_t st);
 cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
                                int slot_stride, unsigned long long epoch, double *acc_out, cudaStream_t st);
@@ -104,6 +113,9 @@ struct K3StepArgs {
   double spec_ca, spec_cb;
   unsigned long long *seq_out = nullptr;   // optional: launch sequence number stored behind the scalars (host polls it)
   unsigned long long seq = 0;
+  XchgGather xg;          // pending exchange whose sums this kernel gathers itself (then `acc` is written, not only read)
+  double *acc_w = nullptr;
+  double *hist_out = nullptr;   // optional (mapped host memory): {loss sum, count} at the second point of the sweep just consumed (AGD.scala:304)
 };
 cudaError_t k3_step_launch(const K3StepArgs &a, cudaStream_t st);
 struct K3GxArgs {
@@ -116,6 +128,8 @@ struct K3GxArgs {
   int32_t d;
   unsigned long long *seq_out = nullptr;
   unsigned long long seq = 0;
+  XchgGather xg;          // as in K3StepArgs
+  double *acc_w = nullptr;
 };
 cudaError_t k3_gx_launch(const K3GxArgs &a, cudaStream_t st);
 // out = a*ca + b*cb (separate roundings, as breeze does at AGD.scala:249)

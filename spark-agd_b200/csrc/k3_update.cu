@@ -41,6 +41,29 @@ __device__ __forceinline__ double prox_elem(int updater, double w, double g, dou
 }
 
 // block reduce NS values, write partials, last block sums partials in block order -> scalars
+// ---- gather half of the peer-memory exchange, inlined into its consumer (see XchgGather)
+__device__ __forceinline__ void xg_wait(const XchgGather &xg) {
+  if (xg.world) {
+    if (threadIdx.x < xg.world) {
+      const volatile unsigned long long *f = xg.flags + xg.buf * xg.world + threadIdx.x;
+      while (*f < xg.epoch) __nanosleep(20);
+      __threadfence_system();   // acquire: the slots this flag guards are read after the CTA barrier
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ double xg_load(const XchgGather &xg, const double *acc, int j) {
+  if (!xg.world) return acc[j];
+  double s = 0.0;
+  for (int r = 0; r < xg.world; ++r) s += __ldcg(xg.xbuf + ((size_t)xg.buf * xg.world + r) * xg.slot_stride + j);  // rank order
+  return s;
+}
+// entries d .. n-1 (loss sums, counts, the second block of a two-gradient sweep) for later readers of acc
+__device__ __forceinline__ void xg_materialize_tail(const XchgGather &xg, double *acc_w, int d) {
+  if (!xg.world) return;
+  for (int c = d + blockIdx.x * kK3Threads + threadIdx.x; c < xg.n; c += gridDim.x * kK3Threads) acc_w[c] = xg_load(xg, acc_w, c);
+}
+
 // block reduce NS values, write partials, last block sums partials in block order -> scalars (mapped pinned host memory).
 // tail != nullptr: scalars[6..7] = tail[0..1] (loss sum, count of the evaluation the kernel consumed).
 // seq_out != nullptr: ONE thread stores every scalar, fences at system scope once, then stores the sequence number of this
@@ -48,7 +71,8 @@ __device__ __forceinline__ double prox_elem(int updater, double w, double g, dou
 template <int NS>
 __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials, unsigned int *ticket,
                                               double *scalars, const int (&slot)[NS], const double *tail = nullptr,
-                                              unsigned long long *seq_out = nullptr, unsigned long long seq = 0ull) {
+                                              unsigned long long *seq_out = nullptr, unsigned long long seq = 0ull,
+                                              const double *tail_vals = nullptr) {
   __shared__ double sh[NS][kK3Threads / 32];
   __shared__ double fin[NS];
   __shared__ bool last;
@@ -83,7 +107,8 @@ __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials,
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int i = 0; i < NS; ++i) scalars[slot[i]] = fin[i];
-      if (tail) { scalars[6] = tail[0]; scalars[7] = tail[1]; }
+      if (tail_vals) { scalars[6] = tail_vals[0]; scalars[7] = tail_vals[1]; }
+      else if (tail) { scalars[6] = tail[0]; scalars[7] = tail[1]; }
       *ticket = 0u;
       if (seq_out) {
         __threadfence_system();
@@ -94,10 +119,19 @@ __device__ __forceinline__ void finish_reduce(double (&v)[NS], double *partials,
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_step_kernel(const K3StepArgs a) {
-  const double count = a.acc[a.d + 1];
+  xg_wait(a.xg);
+  const double count = xg_load(a.xg, a.acc, a.d + 1);
+  __shared__ double tailv[2];
+  if (threadIdx.x == 0) { tailv[0] = xg_load(a.xg, a.acc, a.d); tailv[1] = count; }
+  if (a.hist_out && blockIdx.x == 0 && threadIdx.x == 1) {   // the history evaluation that rode along (:304): straight to the host
+    a.hist_out[0] = xg_load(a.xg, a.acc, a.d + 2);
+    a.hist_out[1] = xg_load(a.xg, a.acc, a.d + 3);
+  }
   double v[6] = {0, 0, 0, 0, 0, 0};
   for (int j = blockIdx.x * kK3Threads + threadIdx.x; j < a.d; j += gridDim.x * kK3Threads) {
-    const double g = __ddiv_rn(a.acc[j], count);                                          // :207
+    const double aj = xg_load(a.xg, a.acc, j);
+    if (a.xg.world) a.acc_w[j] = aj;
+    const double g = __ddiv_rn(aj, count);                                                // :207
     const double xo = a.x_old[j];
     const double z = prox_elem(a.updater, a.z_old[j], g, a.step, a.reg);                  // :254
     const double x = __dadd_rn(__dmul_rn(xo, a.one_minus_theta), __dmul_rn(z, a.theta));  // :255
@@ -115,22 +149,29 @@ __global__ void __launch_bounds__(kK3Threads) k3_step_kernel(const K3StepArgs a)
     v[4] = fma(g, dx, v[4]);
     v[5] += fabs(x);
   }
+  xg_materialize_tail(a.xg, a.acc_w, a.d);
   const int slot[6] = {0, 1, 2, 3, 4, 5};
-  finish_reduce<6>(v, a.partials, a.ticket, a.scalars, slot, a.acc + a.d, a.seq_out, a.seq);
+  finish_reduce<6>(v, a.partials, a.ticket, a.scalars, slot, a.acc + a.d, a.seq_out, a.seq, tailv);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_gx_kernel(const K3GxArgs a) {
-  const double count = a.acc[a.d + 1];
+  xg_wait(a.xg);
+  const double count = xg_load(a.xg, a.acc, a.d + 1);
+  __shared__ double tailv[2];
+  if (threadIdx.x == 0) { tailv[0] = xg_load(a.xg, a.acc, a.d); tailv[1] = count; }
   double v[1] = {0};
   for (int j = blockIdx.x * kK3Threads + threadIdx.x; j < a.d; j += gridDim.x * kK3Threads) {
-    const double g = __ddiv_rn(a.acc[j], count);
+    const double aj = xg_load(a.xg, a.acc, j);
+    if (a.xg.world) a.acc_w[j] = aj;
+    const double g = __ddiv_rn(aj, count);
     a.g_x[j] = g;
     const double xy = __dsub_rn(a.x[j], a.y[j]);
     const double dg = __dsub_rn(g, a.g_y[j]);
     v[0] = fma(xy, dg, v[0]);                                                             // :278
   }
+  xg_materialize_tail(a.xg, a.acc_w, a.d);
   const int slot[1] = {0};
-  finish_reduce<1>(v, a.partials, a.ticket, a.scalars, slot, a.acc + a.d, a.seq_out, a.seq);
+  finish_reduce<1>(v, a.partials, a.ticket, a.scalars, slot, a.acc + a.d, a.seq_out, a.seq, tailv);
 }
 
 __global__ void __launch_bounds__(kK3Threads) k3_prox_kernel(const K3ProxArgs a) {
