@@ -134,6 +134,7 @@ struct agd_handle {
   unsigned long long x_epoch = 0;
   // a sweep whose gather was left to the K3 kernel that consumes it (smooth_device(..., defer_gather))
   bool xg_pending = false;
+  bool xg_rs = false;        // the pending exchange is of the reduce-scatter form
   unsigned long long xg_epoch = 0;
   int xg_n = 0;
   std::string err;
@@ -359,16 +360,17 @@ int ensure_nccl(agd_handle *h) {
 // step 1 of the exchange setup: allocate this process's buffers for the current dimension and describe them
 int xchg_alloc(agd_handle *h, std::vector<XHandles> &mine) {
   const int W = h->world, nd = (int)h->devs.size();
-  const size_t n = 2 * ((size_t)h->d + 4);   // room for a two-gradient sweep
+  const int S = 2 * (h->d + 4);              // slot stride: room for a two-gradient sweep
+  const size_t total = xchg_total_doubles(S, W), nflags = 6 * (size_t)W;   // one-shot + reduce-scatter areas (agd_common.cuh)
   mine.assign((size_t)nd, XHandles());
   for (int i = 0; i < nd; ++i) {
     Dev &D = h->devs[i];
     CK(cudaSetDevice(D.ordinal));
-    CK(cudaMalloc(&D.xbuf, 2 * (size_t)W * n * sizeof(double)));
-    CK(cudaMalloc(&D.xflags, 2 * (size_t)W * sizeof(unsigned long long)));
+    CK(cudaMalloc(&D.xbuf, total * sizeof(double)));
+    CK(cudaMalloc(&D.xflags, nflags * sizeof(unsigned long long)));
     CK(cudaMalloc(&D.xticket, sizeof(unsigned int)));
-    CK(cudaMemset(D.xbuf, 0, 2 * (size_t)W * n * sizeof(double)));
-    CK(cudaMemset(D.xflags, 0, 2 * (size_t)W * sizeof(unsigned long long)));
+    CK(cudaMemset(D.xbuf, 0, total * sizeof(double)));
+    CK(cudaMemset(D.xflags, 0, nflags * sizeof(unsigned long long)));
     CK(cudaMemset(D.xticket, 0, sizeof(unsigned int)));
     memset(&mine[i], 0, sizeof(XHandles));
     mine[i].can_peer = 1;
@@ -572,7 +574,14 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
   const int32_t d = h->d;
   const int32_t n = (dual_full ? 2 : 1) * (d + 4);   // doubles this sweep produces and exchanges
   const bool p2p = h->world > 1 && h->x_p2p;
+  const bool rs = p2p && n >= kXchgRsMin;    // large payloads: reduce-scatter + all-gather instead of the one-shot exchange
   const unsigned long long epoch = p2p ? ++h->x_epoch : 0ull;
+  auto make_rs = [&](Dev &D, size_t i) {
+    XchgRs x;
+    x.peers = D.xpeers; x.world = h->world; x.my_rank = h->first_rank + (int)i; x.buf = (int)(epoch & 1ull);
+    x.n = n; x.slot_stride = 2 * (d + 4); x.epoch = epoch; x.ticket = D.xticket;
+    return x;
+  };
   auto make_pub = [&](Dev &D, size_t i) {
     XchgPub pub;
     pub.peers = D.xpeers; pub.world = h->world; pub.my_rank = h->first_rank + (int)i; pub.buf = (int)(epoch & 1ull);
@@ -594,8 +603,12 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
       CK(k1_csr_launch(a, s.elem_bytes, D.sm_count, D.st));
       if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
-      if (p2p) { const XchgPub pub = make_pub(D, i); CK(xchg_publish_launch(D.acc, pub, D.st)); }
-      h->launches += (i == 0) ? (p2p ? 3 : 2) : 0;
+      if (rs) {
+        const XchgRs x = make_rs(D, i);
+        CK(xchg_rs_publish_launch(D.acc, x, D.st));
+        CK(xchg_rs_reduce_bcast_launch(D.xbuf, D.xflags, x, D.st));
+      } else if (p2p) { const XchgPub pub = make_pub(D, i); CK(xchg_publish_launch(D.acc, pub, D.st)); }
+      h->launches += (i == 0) ? (rs ? 4 : (p2p ? 3 : 2)) : 0;
       continue;
     }
     K1Args a;
@@ -628,13 +641,20 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     else CK(k1_generic_launch(a, eb, D.sm_count, max_blocks, &blocks, D.st));
     if (t0) CK(cudaEventRecord(next_event(D.ev, D.ev_used), D.st));
     if (i == 0) trace_mark(h, dual_full ? "K1x2" : (w2_of ? "K1+loss" : "K1"));
-    if (p2p) { const XchgPub pub = make_pub(D, i); CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, &pub, D.st)); }
+    if (p2p && !rs) { const XchgPub pub = make_pub(D, i); CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, &pub, D.st)); }
     else CK(k1_reduce_launch(D.slabs, blocks, n, D.acc, nullptr, D.st));
+    if (rs) {
+      const XchgRs x = make_rs(D, i);
+      CK(xchg_rs_publish_launch(D.acc, x, D.st));
+      CK(xchg_rs_reduce_bcast_launch(D.xbuf, D.xflags, x, D.st));
+      if (i == 0) h->launches += 2;
+    }
     if (i == 0) trace_mark(h, p2p ? "reduce+publish" : "reduce");
     if (i == 0) h->launches += (s.rows > 0 ? 2 : 1);
   }
   if (p2p && defer_gather) {
     h->xg_pending = true;
+    h->xg_rs = rs;
     h->xg_epoch = epoch;
     h->xg_n = n;
     h->collectives += 1;
@@ -643,7 +663,8 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     for (Dev &D : h->devs) {
       CK(cudaSetDevice(D.ordinal));
-      CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, 2 * (d + 4), epoch, D.acc, D.st));
+      if (rs) CK(xchg_rs_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, 2 * (d + 4), epoch, D.acc, D.st));
+      else CK(xchg_gather_launch(D.xbuf, D.xflags, h->world, (int)(epoch & 1ull), n, 2 * (d + 4), epoch, D.acc, D.st));
     }
     if (timed) { CK(cudaSetDevice(D0.ordinal)); CK(cudaEventRecord(next_event(D0.ev_ar, D0.ev_ar_used), D0.st)); }
     trace_mark(h, "gather");
@@ -1431,8 +1452,11 @@ int agd_run(agd_handle *h, const agd_params *p, const double *w0, double *w_out,
   auto take_gather = [&](Dev &D) {
     XchgGather g;
     if (h->xg_pending) {
-      g.xbuf = D.xbuf; g.flags = D.xflags; g.world = h->world; g.buf = (int)(h->xg_epoch & 1ull); g.n = h->xg_n;
-      g.slot_stride = 2 * (d + 4); g.epoch = h->xg_epoch;
+      const int S = 2 * (d + 4), W = h->world;
+      g.world = W; g.buf = (int)(h->xg_epoch & 1ull); g.n = h->xg_n; g.slot_stride = S; g.epoch = h->xg_epoch;
+      g.rs = h->xg_rs ? 1 : 0;
+      g.xbuf = h->xg_rs ? D.xbuf + xchg_off_res(S, W) : D.xbuf;       // rs: the area of finished sums
+      g.flags = h->xg_rs ? D.xflags + 4 * W : D.xflags;               // rs: the "finished slice arrived" flags
     }
     return g;
   };

@@ -63,11 +63,34 @@ struct XchgPub {
 // the consumer waits for the W flags, adds the W slots in rank order where it needs a value, and writes every one of the n sums
 // to `acc` for later readers.  world == 0: nothing pending, read `acc` as usual.
 struct XchgGather {
-  const double *xbuf = nullptr;               // this device's exchange buffer [2][W][slot_stride]
-  const unsigned long long *flags = nullptr;  // [2][W]
+  const double *xbuf = nullptr;               // this device's exchange buffer [2][W][slot_stride] (one-shot) or its result area (rs)
+  const unsigned long long *flags = nullptr;  // [2][W] of the flag set to wait on
   int world = 0, buf = 0, n = 0, slot_stride = 0;
+  int rs = 0;                                 // 1: reduce-scatter form -- the finished sums sit at xbuf[buf * slot_stride + j]
   unsigned long long epoch = 0;
 };
+// ---- large payloads (n >= kXchgRsMin doubles, e.g. d = 10^6): reduce-scatter + all-gather over the same peer memory.
+// Rank r stores slice p of its partial sums into rank p's `rs` area (slot r), rank p adds the W slots of ITS slice in rank order
+// and stores the finished slice into every rank's `res` area; 2 n / W doubles leave each rank per sweep instead of n W.
+// Layout of one device's exchange allocation (doubles): [one-shot: 2 W S][rs: 2 W L][res: 2 S], S = 2 (d + 4), L = ceil(S / W);
+// flags (u64): [one-shot 2 W][rs arrived 2 W][res arrived 2 W].
+constexpr int kXchgRsMin = 32768;
+struct XchgRs {
+  XchgPeers peers;
+  int world, my_rank, buf, n;
+  int slot_stride;              // S
+  unsigned long long epoch;
+  unsigned int *ticket;
+};
+cudaError_t xchg_rs_publish_launch(const double *acc, const XchgRs &x, cudaStream_t st);
+cudaError_t xchg_rs_reduce_bcast_launch(const double *xbuf_local, const unsigned long long *flags_local, const XchgRs &x, cudaStream_t st);
+// waits for the W finished slices and copies them to acc_out (stand-alone form of the rs gather)
+cudaError_t xchg_rs_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
+                                  int slot_stride, unsigned long long epoch, double *acc_out, cudaStream_t st);
+inline size_t xchg_rs_slice(int S, int W) { return ((size_t)S + W - 1) / W; }
+inline size_t xchg_off_rs(int S, int W) { return 2 * (size_t)W * S; }
+inline size_t xchg_off_res(int S, int W) { return xchg_off_rs(S, W) + 2 * (size_t)W * xchg_rs_slice(S, W); }
+inline size_t xchg_total_doubles(int S, int W) { return xchg_off_res(S, W) + 2 * (size_t)S; }
 cudaError_t xchg_publish_launch(const double *acc, const XchgPub &pub, cudaStream_t st);
 cudaError_t xchg_gather_launch(const double *xbuf_local, const unsigned long long *flags_local, int world, int buf, int n,
                                int slot_stride, unsigned long long epoch, double *acc_out, cudaStream_t st);

@@ -45,7 +45,7 @@ __device__ __forceinline__ double prox_elem(int updater, double w, double g, dou
 __device__ __forceinline__ void xg_wait(const XchgGather &xg) {
   if (xg.world) {
     if (threadIdx.x < xg.world) {
-      const volatile unsigned long long *f = xg.flags + xg.buf * xg.world + threadIdx.x;
+      const volatile unsigned long long *f = xg.flags + xg.buf * xg.world + threadIdx.x;   // flags already points at the right set
       while (*f < xg.epoch) __nanosleep(20);
       __threadfence_system();   // acquire: the slots this flag guards are read after the CTA barrier
     }
@@ -54,6 +54,7 @@ __device__ __forceinline__ void xg_wait(const XchgGather &xg) {
 }
 __device__ __forceinline__ double xg_load(const XchgGather &xg, const double *acc, int j) {
   if (!xg.world) return acc[j];
+  if (xg.rs) return __ldcg(xg.xbuf + (size_t)xg.buf * xg.slot_stride + j);   // reduce-scatter form: the finished sum
   double s = 0.0;
   for (int r = 0; r < xg.world; ++r) s += __ldcg(xg.xbuf + ((size_t)xg.buf * xg.world + r) * xg.slot_stride + j);  // rank order
   return s;

@@ -22,6 +22,17 @@ def make_data(n, d, seed):
     return X, y
 
 
+def make_csr(n, d, k, seed):
+    """n rows with k stored entries each (strictly increasing columns), hinge-style labels."""
+    rng = np.random.default_rng(seed)
+    idx = np.sort(np.stack([rng.choice(d, k, replace=False) for _ in range(512)]), axis=1).astype(np.int32)
+    idx = idx[rng.integers(0, 512, size=n)]
+    val = rng.standard_normal((n, k)).astype(np.float32)
+    w_true = rng.standard_normal(d)
+    y = (np.einsum("ij,ij->i", val.astype(np.float64), w_true[idx]) + 0.3 * rng.standard_normal(n) > 0).astype(np.float64)
+    return np.arange(n + 1, dtype=np.int64) * k, idx, val, y
+
+
 def main():
     rank, world, port, dev, transport, out = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5], sys.argv[6]
     import torch
@@ -67,6 +78,19 @@ def main():
     ws, hs, ss = S.run_with_stats(syn, S.LogisticGradient(), S.SimpleUpdater(), 0.0, 5, 0.0, np.zeros(512))
     res["synthetic"] = {"w": ws.tolist(), "hist": hs.tolist(), "passes": ss.passes, "rows_local": syn.local_rows(0)}
     syn.close()
+    # a wide sparse shard: d + 4 = 100004 doubles per sweep takes the reduce-scatter + all-gather form of the exchange
+    n3, d3, k3 = 9000, 100000, 12
+    rp, ix, va, y3 = make_csr(n3, d3, k3, 13)
+    lo, hi = rank * n3 // world, (rank + 1) * n3 // world
+    wide = ctx.parallelize_csr(y3[lo:hi], rp[lo:hi + 1] - rp[lo], ix[lo:hi].ravel(), va[lo:hi].ravel(), d3, store="f32")
+    w3 = np.random.default_rng(17).standard_normal(d3) * 0.1
+    l3, g3, c3 = wide.smooth(S.HingeGradient(), w3)
+    ww, hw, sw = S.run_with_stats(wide, S.HingeGradient(), S.SquaredL2Updater(), 0.0, 5, 0.05, np.zeros(d3))
+    wm3, hm3, sm3 = S.run_with_stats(wide, S.HingeGradient(), S.SquaredL2Updater(), 0.0, 5, 0.05, np.zeros(d3), memoize=True)
+    res["wide"] = {"loss": l3, "grad_l2": float(np.linalg.norm(g3)), "grad_head": g3[:64].tolist(), "count": c3,
+                   "w_l2": float(np.linalg.norm(ww)), "w_head": ww[:64].tolist(), "hist": hw.tolist(), "passes": sw.passes,
+                   "collective_kind": sw.collective_kind, "memo_hist": hm3.tolist(), "memo_w_l2": float(np.linalg.norm(wm3))}
+    wide.close()
     if rank == 0:
         with open(out, "w") as f:
             json.dump(res, f)

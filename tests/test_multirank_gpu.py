@@ -16,7 +16,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from mp_worker import make_data  # noqa: E402
+from mp_worker import make_csr, make_data  # noqa: E402
 
 
 def _gpu_count():
@@ -103,3 +103,20 @@ def test_process_per_rank_world_matches_oracle(oracle, tmp_path, transport, worl
     np.testing.assert_allclose(res["synthetic"]["hist"], refs.loss_history, rtol=1e-11)
     assert np.linalg.norm(np.array(res["synthetic"]["w"]) - refs.weights) <= 1e-9 * np.linalg.norm(refs.weights)
     assert res["synthetic"]["passes"] == refs.passes
+    # --- a wide sparse shard (d = 100000): the exchange takes its reduce-scatter + all-gather form (n >= 32768 doubles)
+    rp, ix, va, y3 = make_csr(9000, 100000, 12, 13)
+    D3 = O.Data(y3, csr=(rp, ix.ravel(), va.ravel()), d=100000)
+    w3 = np.random.default_rng(17).standard_normal(100000) * 0.1
+    l3, g3, c3 = O.smooth(D3, "hinge", w3, partitions=world, threads=world)
+    wd = res["wide"]
+    assert wd["count"] == c3 == 9000 and wd["collective_kind"] == 1
+    assert abs(wd["loss"] - l3) <= 1e-12 * abs(l3)
+    assert abs(wd["grad_l2"] - np.linalg.norm(g3)) <= 1e-12 * np.linalg.norm(g3)
+    np.testing.assert_allclose(wd["grad_head"], g3[:64], rtol=0, atol=1e-12 * np.max(np.abs(g3)))
+    ref3 = O.agd_run(D3, "hinge", "squared_l2", np.zeros(100000), convergence_tol=0.0, num_iterations=5, reg_param=0.05,
+                     partitions=world, threads=world)
+    np.testing.assert_allclose(wd["hist"], ref3.loss_history, rtol=1e-10)
+    np.testing.assert_allclose(wd["memo_hist"], ref3.loss_history, rtol=1e-10)
+    assert abs(wd["w_l2"] - np.linalg.norm(ref3.weights)) <= 1e-9 * np.linalg.norm(ref3.weights)
+    assert abs(wd["memo_w_l2"] - np.linalg.norm(ref3.weights)) <= 1e-9 * np.linalg.norm(ref3.weights)
+    np.testing.assert_allclose(wd["w_head"], ref3.weights[:64], rtol=0, atol=1e-9 * np.max(np.abs(ref3.weights)))
