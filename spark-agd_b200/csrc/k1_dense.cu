@@ -765,7 +765,8 @@ template <typename T>
 cudaError_t launch_ring_t(const K1Args &a, const RingShape &sh, int nvec, int sm_count, int *blocks_out,
                           cudaStream_t st) {
   if (a.w2 && a.dual_full) {  // two full evaluations per sweep (speculative sweep of the memoised pass structure)
-    if (sh.v != 1) return cudaErrorInvalidValue;   // wide threads have no registers for a second gradient
+    if (sh.v == 4) return cudaErrorInvalidValue;   // four vectors per thread: no registers for a second gradient
+    if (sh.v == 2) return launch_ring_inst<T, 256, 256, 2, 4, 2, 2>(a, nvec, sm_count, blocks_out, st);
     if (sh.tpr == 128) return launch_ring_inst<T, 256, 128, 1, 8, 2, 2>(a, nvec, sm_count, blocks_out, st);
     if (sh.tpr == 256) return launch_ring_inst<T, 256, 256, 1, 8, 2, 2>(a, nvec, sm_count, blocks_out, st);
     return cudaErrorInvalidValue;
@@ -825,6 +826,7 @@ int k1_ring_dual_full_supported(int32_t d, int elem_bytes) {
   RingShape sh;
   int nvec;
   if ((elem_bytes != 4 && elem_bytes != 8) || !ring_shape(d, elem_bytes, sh, nvec)) return 0;
+  if (sh.v == 2) return 1;                                          // two vectors per thread: d <= 2048 (fp32) / 1024 (fp64)
   return sh.v == 1 && (sh.tpr == 128 || sh.tpr == 256) ? 1 : 0;   // one vector per thread: d <= 1024 (fp32) / 512 (fp64)
 }
 

@@ -467,7 +467,7 @@ def test_smooth_pair_equals_two_sweeps_bit_for_bit(agd, ctx, grad, shape, store,
 
 
 TWO_SHAPES = [((3001, 1024), "f32"), ((2000, 512), "f32"), ((501, 1001), "f32"), ((1500, 512), "f64"), ((700, 300), "f64"),
-              ((16, 1024), "f32"), ((9, 640), "f32")]
+              ((16, 1024), "f32"), ((9, 640), "f32"), ((1200, 1024), "f64"), ((900, 2048), "f32"), ((333, 1500), "f32")]
 
 
 @pytest.mark.parametrize("grad", GRADS)
@@ -494,9 +494,9 @@ def test_smooth_two_equals_two_sweeps_bit_for_bit(agd, ctx, grad, shape, store):
 
 def test_smooth_two_unsupported_shards_refuse(agd, ctx):
     rng = np.random.default_rng(5)
-    X = rng.standard_normal((300, 2048)).astype(np.float32)
+    X = rng.standard_normal((300, 4096)).astype(np.float32)
     y = (rng.random(300) > 0.5).astype(np.float64)
-    for store, dd in (("f32", 2048), ("bf16", 1024)):        # wide threads / tcgen05 path: no two-gradient form
+    for store, dd in (("f32", 4096), ("bf16", 1024)):        # four vectors per thread / tcgen05 path: no two-gradient form
         ds = ctx.parallelize(y, X[:, :dd].copy(), store=store)
         with pytest.raises(agd.NativeError, match="two-(gradient|point)"):
             ds.smooth_two(agd.LogisticGradient(), np.zeros(dd), np.zeros(dd))
@@ -534,7 +534,7 @@ def test_speculative_memoised_run_is_bit_identical(agd, ctx, case):
     rounds = sm.iterations + sm.backtracks
     assert sm.k1_launches < s0.k1_launches
     assert sm.k1_launches <= 2 * rounds - sm.fused_passes - max(0, sm.restarts - 1)
-    if d * (4 if store == "f32" else 8) > 1024 and d * (4 if store == "f32" else 8) <= 4096:   # shapes with a two-gradient kernel
+    if d * (4 if store == "f32" else 8) > 1024 and d * (4 if store == "f32" else 8) <= 8192:   # shapes with a two-gradient kernel
         assert sm.fused_passes > 0
     wn, hn, sn = agd.run_with_stats(*args, memoize=True, fuse=False)    # AGD_FLAG_NO_FUSE switches the speculation off as well
     assert np.array_equal(wn, w0) and np.array_equal(hn, h0) and sn.fused_passes == 0
