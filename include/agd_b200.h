@@ -188,7 +188,7 @@ int agd_smooth_pair(agd_handle *h, int32_t gradient, const double *w, const doub
 /* Two complete applySmooth evaluations (loss and gradient at w AND at w2) from ONE sweep over the shards -- what agd_run's
  * memoised pass structure uses to evaluate applySmooth(x) of the backtracking test (AGD.scala:269) together with
  * applySmooth(y) of the next iteration (:250).  Bit for bit what two agd_smooth calls return.  Dense fp32 / fp64 shards with
- * at most 512 16-byte vectors per row (d <= 2048 fp32, <= 1024 fp64); fails elsewhere. */
+ * at most 512 16-byte vectors per row (d <= 2048 fp32, <= 1024 fp64) and bf16 shards on the tcgen05 kernel; fails elsewhere. */
 int agd_smooth_two(agd_handle *h, int32_t gradient, const double *w, const double *w2, double *loss, double *grad,
                    int64_t *count, double *loss2, double *grad2);
 /* agd_prox = applyProjector (AGD.scala:214-222): Updater.compute(w, g, step, iter = 1, reg). */

@@ -557,7 +557,9 @@ bool dual_full_supported(const agd_handle *h) {
     const Shard &s = D.sh;
     if (s.csr) return false;
     const int eb = s.elem_bytes ? s.elem_bytes : 4;
-    if (dense_kernel_of(h, eb) != 1 || !k1_ring_dual_full_supported(h->d, eb)) return false;
+    const int k = dense_kernel_of(h, eb);
+    if (k == 3) { if (h->tune_rows != 0 || h->tc_margins_f64) return false; continue; }   // tcgen05: default mapping has one
+    if (k != 1 || !k1_ring_dual_full_supported(h->d, eb)) return false;
   }
   return h->k1_diag == 0;
 }
@@ -625,7 +627,7 @@ int smooth_device(agd_handle *h, int kind, WSel w_of, bool timed, WSel w2_of = n
     if (h->k1_variant == 1 && !ring) return fail(h, "ring kernel does not support d=%d with %d-byte elements", d, eb);
     if (a.w2 && ((tc && (h->tune_rows != 0 || h->tc_margins_f64)) || (!tc && ring && !k1_ring_dual_supported(d, eb))))
       return fail(h, "internal: two-point sweep requested on a kernel without one");
-    if (dual_full && (tc || !ring || !k1_ring_dual_full_supported(d, eb)))
+    if (dual_full && ((tc && (h->tune_rows != 0 || h->tc_margins_f64)) || (!tc && (!ring || !k1_ring_dual_full_supported(d, eb)))))
       return fail(h, "internal: two-gradient sweep requested on a kernel without one");
     int max_blocks = k1_max_blocks(D.sm_count);
     if (!ring) {  // generic: bound the slab memory for very wide rows

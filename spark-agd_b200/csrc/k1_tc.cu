@@ -33,6 +33,7 @@ constexpr int kKR = 16;            // rows per tile = K of one MMA
 // launch).  RPT = 4: 256 consumers, each w value fetched from shared memory serves four rows instead of two -- the kernel is
 // bound by shared-memory bandwidth (TMA writes + MMA operand reads + x reads + w reads), and w is the largest reader.
 constexpr int kRegsConsumer = 64, kRegsAux = 56, kRegsFlush = 112;
+constexpr int kRegsFlush2 = 168;   // two-gradient form: 80 + everything released by 512 consumers (16 each) and 128 aux threads (24 each)
 constexpr int kFlush = 8;          // tiles between TMEM -> fp64 flushes (128 rows of fp32 accumulation)
 constexpr int kBlockBytes = kKR * 128;     // one [16 rows][64 features] swizzled block
 
@@ -135,7 +136,10 @@ __device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
 // the same class as the gradient of this kernel (bf16 x 3 split, fp32 TMEM sums).  F32 = false keeps fp64-exact margins.
 // DUAL (F32 mapping only): the loss is also evaluated at a second point w2 from the same tile -- one more packed FMA per
 // feature pair in phase 1, lanes 16-31 of the scalar warp -- with bits identical to a launch of its own at w2.
-template <int RPT, bool F32, bool DUAL = false>
+// DUAL == 2: the GRADIENT at w2 as well (two-gradient sweep): r at w2 takes columns 3-5 of the same B operand, so the second
+// X^T r costs no extra MMA at all -- the tensor core computes 16 columns either way; the flush reads 8 TMEM columns
+// instead of 4 and keeps a second fp64 gradient (setmaxnreg gives the flush warpgroup everything the others released).
+template <int RPT, bool F32, int DUAL = 0>
 __global__ void __launch_bounds__(tc_consumers(RPT) + 256, 1)
 k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap3, const TcArgs a,
              const long long ntiles) {
@@ -286,14 +290,14 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
       }
       named_arrive(3 + bb, kConsumers + 32);                   // partial[bb] may be overwritten
       if (k >= 2) mbar_wait(b2_empty + 8u * bb, (uint32_t)(((k >> 1) - 1) & 1));  // MMAs of tile k-2 have read b2[bb]
-      if (lane < kKR) {
-        // r_i -> three bf16 pieces; element (n, row) of the K-major B operand
+      if (lane < kKR || (DUAL == 2 && second)) {
+        // r_i -> three bf16 pieces; element (n, row) of the K-major B operand (n = 0..2 at w, 3..5 at w2)
         const __nv_bfloat16 hi = __double2bfloat16(mult);
         const double r1 = mult - (double)__bfloat162float(hi);
         const __nv_bfloat16 mid = __double2bfloat16(r1);
         const double r2 = r1 - (double)__bfloat162float(mid);
         const __nv_bfloat16 lo = __double2bfloat16(r2);
-        unsigned char *base = b2 + bb * 512 + (lane / 8) * 128 + (lane % 8) * 2;
+        unsigned char *base = b2 + bb * 512 + (srow / 8) * 128 + (srow % 8) * 2 + (second ? 3 * 16 : 0);
         *reinterpret_cast<__nv_bfloat16 *>(base + 0 * 16) = hi;
         *reinterpret_cast<__nv_bfloat16 *>(base + 1 * 16) = mid;
         *reinterpret_cast<__nv_bfloat16 *>(base + 2 * 16) = lo;
@@ -309,15 +313,25 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
       cntacc += __shfl_xor_sync(0xffffffffu, cntacc, off);
     }
     if (lane == 0) { slab[a.d] = lossacc; slab[a.d + 1] = cntacc; if (!DUAL) { slab[a.d + 2] = 0.0; slab[a.d + 3] = 0.0; } }
-    if (DUAL && lane == kKR) { slab[a.d + 2] = lossacc; slab[a.d + 3] = cntacc; }
+    if (DUAL && lane == kKR) {
+      slab[a.d + 2] = lossacc; slab[a.d + 3] = cntacc;
+      if (DUAL == 2) {   // second block: [gradient at w2 | loss sum | count | 0 | 0]
+        double *slab2 = slab + a.d + 4;
+        slab2[a.d] = lossacc; slab2[a.d + 1] = cntacc; slab2[a.d + 2] = 0.0; slab2[a.d + 3] = 0.0;
+      }
+    }
    }
   } else if (warp >= kCW + 4) {
-    // ===================== flush warpgroup: owns the fp64 gradient, drains TMEM every kFlush tiles ==========
-    if (kRepartition) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsFlush));
+    // ===================== flush warpgroup: owns the fp64 gradient(s), drains TMEM every kFlush tiles ==========
+    if (kRepartition) {
+      if (DUAL == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsFlush2));
+      else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsFlush));
+    }
     const int fw = warp - (kCW + 4);   // TMEM lanes 32*fw .. 32*fw+31 (kCW + 4 is a multiple of 4)
     double gacc[32];                // feature (c*128 + 32*fw + lane), c < d/128
+    double gacc2[DUAL == 2 ? 32 : 1];   // the same at w2
 #pragma unroll
-    for (int c = 0; c < 32; ++c) gacc[c] = 0.0;
+    for (int c = 0; c < 32; ++c) { gacc[c] = 0.0; if (DUAL == 2) gacc2[DUAL == 2 ? c : 0] = 0.0; }
     uint32_t done_parity = 0;
     for (long long k = 0; k < my_tiles; ++k) {
       if (((k + 1) % kFlush) == 0 || k + 1 == my_tiles) {
@@ -327,13 +341,23 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           if (c < nch) {
-            uint32_t v0, v1, v2, v3;
             const uint32_t taddr = tmem_base + ((uint32_t)(fw * 32) << 16) + (uint32_t)c * 16u;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                         : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            gacc[c] += ((double)__uint_as_float(v0) + (double)__uint_as_float(v1)) + (double)__uint_as_float(v2);
+            if (DUAL == 2) {
+              uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                           : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3), "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7)
+                           : "r"(taddr));
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              gacc[c] += ((double)__uint_as_float(v0) + (double)__uint_as_float(v1)) + (double)__uint_as_float(v2);
+              gacc2[DUAL == 2 ? c : 0] += ((double)__uint_as_float(v3) + (double)__uint_as_float(v4)) + (double)__uint_as_float(v5);
+            } else {
+              uint32_t v0, v1, v2, v3;
+              asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                           : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                           : "r"(taddr));
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              gacc[c] += ((double)__uint_as_float(v0) + (double)__uint_as_float(v1)) + (double)__uint_as_float(v2);
+            }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;");
@@ -343,7 +367,10 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     }
 #pragma unroll
     for (int c = 0; c < 32; ++c)
-      if (c < nch) slab[c * 128 + fw * 32 + lane] = gacc[c];
+      if (c < nch) {
+        slab[c * 128 + fw * 32 + lane] = gacc[c];
+        if (DUAL == 2) slab[a.d + 4 + c * 128 + fw * 32 + lane] = gacc2[DUAL == 2 ? c : 0];
+      }
   } else {
     // ===================== consumers: phase 1 in fp64, straight out of the swizzled tile =====================
     if (kRepartition) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
@@ -654,25 +681,29 @@ cudaError_t k1_tc_launch(const K1Args &a, int sm_count, int *blocks_out, cudaStr
   const int smem_bytes = (int)L.total + 1024;
   cudaError_t e;
   if (a.tune_rows == 1) {  // option ring_rows=1: row-per-lane consumers (broadcast w reads; measured slower)
-    e = set_smem_once<1>(k1_tc_kernel<0, false>, smem_bytes);
+    e = set_smem_once<1>(k1_tc_kernel<0, false, 0>, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<0, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<0, false, 0><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.tune_rows == 4) {  // option ring_rows=4: 256 consumers with four rows each (measured slower)
-    e = set_smem_once<2>(k1_tc_kernel<4, false>, smem_bytes);
+    e = set_smem_once<2>(k1_tc_kernel<4, false, 0>, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<4, false><<<(unsigned)grid, 512, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<4, false, 0><<<(unsigned)grid, 512, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.tc_margins_f64) {  // option tc_margins=f64: 512 consumers, two rows per thread, fp64-exact margins
-    e = set_smem_once<3>(k1_tc_kernel<2, false>, smem_bytes);
+    e = set_smem_once<3>(k1_tc_kernel<2, false, 0>, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<2, false><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<2, false, 0><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+  } else if (a.w2 && a.dual_full) {  // the default mapping + loss AND gradient at a second point (speculative sweep)
+    e = set_smem_once<6>(k1_tc_kernel<2, true, 2>, smem_bytes);
+    if (e != cudaSuccess) return e;
+    k1_tc_kernel<2, true, 2><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else if (a.w2) {  // the default mapping + the loss at a second point (pass fusion)
-    e = set_smem_once<4>(k1_tc_kernel<2, true, true>, smem_bytes);
+    e = set_smem_once<4>(k1_tc_kernel<2, true, 1>, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<2, true, true><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<2, true, 1><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   } else {  // default: the same mapping with fp32 phase-1 arithmetic (packed FFMA2, no fp64 conversion per element)
-    e = set_smem_once<5>(k1_tc_kernel<2, true>, smem_bytes);
+    e = set_smem_once<5>(k1_tc_kernel<2, true, 0>, smem_bytes);
     if (e != cudaSuccess) return e;
-    k1_tc_kernel<2, true><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
+    k1_tc_kernel<2, true, 0><<<(unsigned)grid, 768, smem_bytes, st>>>(tmap, tmap3, t, ntiles);
   }
   return cudaGetLastError();
 }

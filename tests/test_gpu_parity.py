@@ -467,7 +467,8 @@ def test_smooth_pair_equals_two_sweeps_bit_for_bit(agd, ctx, grad, shape, store,
 
 
 TWO_SHAPES = [((3001, 1024), "f32"), ((2000, 512), "f32"), ((501, 1001), "f32"), ((1500, 512), "f64"), ((700, 300), "f64"),
-              ((16, 1024), "f32"), ((9, 640), "f32"), ((1200, 1024), "f64"), ((900, 2048), "f32"), ((333, 1500), "f32")]
+              ((16, 1024), "f32"), ((9, 640), "f32"), ((1200, 1024), "f64"), ((900, 2048), "f32"), ((333, 1500), "f32"),
+              ((2000, 1024), "bf16"), ((517, 4096), "bf16"), ((300, 128), "bf16")]     # tcgen05: r at w2 rides in B columns 3-5
 
 
 @pytest.mark.parametrize("grad", GRADS)
@@ -496,8 +497,10 @@ def test_smooth_two_unsupported_shards_refuse(agd, ctx):
     rng = np.random.default_rng(5)
     X = rng.standard_normal((300, 4096)).astype(np.float32)
     y = (rng.random(300) > 0.5).astype(np.float64)
-    for store, dd in (("f32", 4096), ("bf16", 1024)):        # four vectors per thread / tcgen05 path: no two-gradient form
+    for store, dd in (("f32", 4096), ("bf16", 1024)):        # four vectors per thread / tcgen05 with fp64 margins: no two-gradient form
         ds = ctx.parallelize(y, X[:, :dd].copy(), store=store)
+        if store == "bf16":
+            ds.set_option("tc_margins", "f64")
         with pytest.raises(agd.NativeError, match="two-(gradient|point)"):
             ds.smooth_two(agd.LogisticGradient(), np.zeros(dd), np.zeros(dd))
         # the memoised run simply does not speculate there
@@ -511,7 +514,9 @@ SPEC_CASES = [(20000, 1024, "logistic", "simple", 0.0, "f32", 12, {}),
               (5000, 512, "hinge", "squared_l2", 0.1, "f32", 15, {}),
               (4000, 256, "least_squares", "simple", 0.0, "f64", 25, {"L0": 1e-3}),                 # L-increase: guesses rejected
               (1000, 100, "least_squares", "squared_l2", 0.1, "f64", 30, {}),                       # restarts: (f_x, g_x) reused
-              (1000, 512, "least_squares", "simple", 0.0, "f64", 60, {"tol": 1e-6})]               # leaves through :322-324
+              (1000, 512, "least_squares", "simple", 0.0, "f64", 60, {"tol": 1e-6}),               # leaves through :322-324
+              (5000, 1024, "logistic", "simple", 0.0, "bf16", 8, {}),                               # tcgen05 kernel, two-gradient form
+              (3000, 4096, "least_squares", "squared_l2", 0.01, "bf16", 8, {})]
 
 
 @pytest.mark.parametrize("case", SPEC_CASES, ids=[f"{c[0]}x{c[1]}-{c[2]}-{c[3]}-{i}" for i, c in enumerate(SPEC_CASES)])
@@ -521,7 +526,7 @@ def test_speculative_memoised_run_is_bit_identical(agd, ctx, case):
     bit for bit; one sweep per accepted iteration."""
     n, d, grad, upd, reg, store, iters, kw = case
     rng = np.random.default_rng(n + d + iters + 19)
-    X, y = make_data(rng, n, d, grad, np.float32 if store == "f32" else np.float64)
+    X, y = make_data(rng, n, d, grad, np.float64 if store == "f64" else np.float32)
     data = ctx.parallelize(y, X, store=store)
     args = (data, G(agd, grad), U(agd, upd), kw.get("tol", 0.0), iters, reg, np.zeros(d), kw.get("L0", 1.0),
             kw.get("Lexact", float("inf")), kw.get("beta", 0.5), kw.get("alpha", 0.9), kw.get("may_restart", True))
@@ -534,7 +539,8 @@ def test_speculative_memoised_run_is_bit_identical(agd, ctx, case):
     rounds = sm.iterations + sm.backtracks
     assert sm.k1_launches < s0.k1_launches
     assert sm.k1_launches <= 2 * rounds - sm.fused_passes - max(0, sm.restarts - 1)
-    if d * (4 if store == "f32" else 8) > 1024 and d * (4 if store == "f32" else 8) <= 8192:   # shapes with a two-gradient kernel
+    row_bytes = d * {"f32": 4, "f64": 8, "bf16": 2}[store]
+    if store == "bf16" or 1024 < row_bytes <= 8192:                # shapes with a two-gradient kernel
         assert sm.fused_passes > 0
     wn, hn, sn = agd.run_with_stats(*args, memoize=True, fuse=False)    # AGD_FLAG_NO_FUSE switches the speculation off as well
     assert np.array_equal(wn, w0) and np.array_equal(hn, h0) and sn.fused_passes == 0
